@@ -1,0 +1,172 @@
+/*
+ * onssen_b200 -- C ABI of the B200 (sm_100a) STFT-mask separation hot path.
+ *
+ * The reference (speechLabBcCuny/onssen) is pure Python/PyTorch: it has no FFI of its own.  Every entry
+ * point below therefore cites the reference *Python call site* whose arithmetic it replaces; the
+ * reference-side binding (ctypes) is shown in INTEGRATION.md and implemented in onssen_b200/_lib.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - every function returns ONSSEN_OK (0) or a negative ONSSEN_ERR_* code; nothing throws, nothing
+ *     allocates, no hidden global state (except per-process device attribute caches)
+ *   - tensors are dense row-major; "time-major" means row index m = t * B + b
+ *   - Hp = 32*ceil(H/32) is the hidden size padded to whole 32-unit row blocks; "packed" LSTM buffers
+ *     use the layouts documented at onssen_lstm_pack_* 
+ */
+#ifndef ONSSEN_B200_H_
+#define ONSSEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONSSEN_OK 0
+#define ONSSEN_ERR_ARG (-1)         /* bad argument (null, misaligned, size) */
+#define ONSSEN_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define ONSSEN_ERR_CUDA (-3)        /* CUDA runtime launch/config error (see cudaGetLastError) */
+#define ONSSEN_ERR_DRIVER (-4)      /* cuTensorMapEncodeTiled unavailable / failed */
+#define ONSSEN_ERR_RESIDENCY (-5)   /* persistent recurrent grid does not fit on the device */
+
+/* label dtypes accepted by the loss kernels (reference labels are float64, feature_utils.py:86) */
+#define ONSSEN_DT_F32 0
+#define ONSSEN_DT_F64 1
+#define ONSSEN_DT_U8 2
+
+const char* onssen_version(void);
+const char* onssen_error_string(int code);
+/* number of SMs of the current device (cached) */
+int onssen_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * STFT featurizer  (replaces onssen/data/feature_utils.py:5-21,49-95 + the crop/tile logic of
+ * onssen/data/wsj0_2mix.py:114-152, executed per batch on the device instead of per item on the host)
+ *
+ * wav_*      [B][nsample] float32 waveforms (mix, s1, s2); s1/s2 may be NULL when no label output needs them
+ * crop_start [B] int32 first frame of the crop in the (possibly tiled) frame sequence
+ *            (reference: np.random.randint(frames - T), wsj0_2mix.py:125) -- explicit so indexing is exact
+ * n_fft in {64..2048, power of two}; frames = 1 + nsample/hop (center=True, reflect padding, periodic Hann);
+ * when frames <= T the STFT is tiled (frame f -> f % frames), wsj0_2mix.py:118-123.
+ * Outputs (any may be NULL): all float32
+ *   feature  [B][T][F]   log10(|mix| + 1e-7)            feature_utils.py:49-51
+ *   mag_mix, mag_s1, mag_s2 [B][T][F]                   wsj0_2mix.py:132-134
+ *   cos_s1, cos_s2 [B][T][F]  cos(angle(mix)-angle(s))  feature_utils.py:67-80
+ *   ph_mix, ph_s1, ph_s2 [B][T][F][2]  (re, im)         feature_utils.py:54-64
+ *   feat_max [B]  per-utterance max of `feature` over the crop (input of the VAD threshold)
+ * F = n_fft/2 + 1.
+ */
+int onssen_stft_features(const float* wav_mix, const float* wav_s1, const float* wav_s2, int B, int nsample,
+                         int n_fft, int hop, const int32_t* crop_start, int T, float* feature, float* mag_mix,
+                         float* mag_s1, float* mag_s2, float* cos_s1, float* cos_s2, float* ph_mix,
+                         float* ph_s1, float* ph_s2, float* feat_max, void* stream);
+
+/* Ideal-binary labels + VAD  (replaces get_one_hot, feature_utils.py:83-95).
+ * one_hot [B][T][F][2] written as out_dtype (ONSSEN_DT_*): argmax over (mag_s1, mag_s2) (ties -> 0),
+ * zeroed where feature < feat_max[b] - db_threshold/20 (strict <). Bit-exact integer result. */
+int onssen_one_hot_vad(const float* feature, const float* mag_s1, const float* mag_s2, const float* feat_max,
+                       float db_threshold, int B, int T, int F, void* one_hot, int out_dtype, void* stream);
+
+/* Masked iSTFT overlap-add (replaces stft_mix*mask -> librosa.core.istft(..., hop_length, length=nsample),
+ * egs/wsj0-2mix/deep_clustering/evaluate.py:42-45, chimera/evaluate.py:40-43).
+ * stft_re/stft_im [B][frames][F]; mask [B][S][frames][F] (NULL = all ones); out [B][S][nsample] float32.
+ * Periodic Hann synthesis window, window-sum-square normalisation, centre trim n_fft/2. */
+size_t onssen_istft_scratch_bytes(int B, int S, int frames, int n_fft);
+int onssen_istft_masked(const float* stft_re, const float* stft_im, const float* mask, int B, int S, int frames,
+                        int n_fft, int hop, int nsample, float* out, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BLSTM stack (replaces torch.nn.LSTM(bidirectional=True, batch_first=True) as called at
+ * onssen/nn/deep_clustering.py:34-35, chimera.py:35-36, enhancement.py:43-44, phase_network.py:50,57).
+ * Gate order i,f,g,o; h0 = c0 = 0.
+ */
+
+/* x [B][T][I] float32 (batch-first, reference layout) -> xh [T*B][Kp] fp16 time-major, zero padded,
+ * Kp = 64*ceil(I/64). */
+int onssen_pack_input_f16(const float* x, int B, int T, int I, void* xh, int Kp, void* stream);
+
+/* Pack one layer's weights for both directions.
+ *   w_ih_{f,r} [4H][I], w_hh_{f,r} [4H][H], b_ih_*, b_hh_* [4H]   (PyTorch parameter layout, fp32)
+ *   in_is_blstm: 0 -> input index k maps to column k (layer 0), Kp = 64*ceil(I/64)
+ *                1 -> I == 2*Hin; input index j maps to column (j/Hin)*Hinp + j%Hin, Kp = 2*Hinp
+ * Outputs:
+ *   wih_p  [2*4Hp][Kp] fp16, row n = dir*4Hp + rb*128 + 4*ul + gate  <->  source row gate*H + rb*32 + ul
+ *   whh_p  [2][Hp/32][Hp/8][128][8] fp16 (per (dir,row-block) a contiguous slab in the no-swizzle UMMA
+ *          K-major core-matrix layout: [k/8][row][k%8]), same row permutation, zero padded
+ *   bias_p [2*4Hp] fp32 = b_ih + b_hh, same permutation
+ */
+int onssen_lstm_pack_layer(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                           const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r,
+                           int H, int I, int in_is_blstm, int Hin, void* wih_p, void* whh_p, float* bias_p,
+                           void* stream);
+
+/* fp16 tensor-core GEMM with fused epilogue: out = epi(A[M][K] * W[N][K]^T + bias).
+ * epi: 0 none, 1 sigmoid, 2 relu, 3 L2-normalise consecutive groups of `group` columns
+ * (F.normalize eps 1e-12, deep_clustering.py:41). remap_inner>0: time-major row m=t*B+b (inner=B,outer=T)
+ * is written to batch-first output row b*T+t. lda/ldw in elements (multiples of 8). */
+int onssen_gemm_l2norm_supported(int group); /* 1 if epi=3 is fused for this group size */
+int onssen_gemm_f16(const void* A, const void* W, const float* bias, float* out, int M, int N, int K,
+                    long long lda, long long ldw, long long ld_out, int epi, int group, int remap_inner,
+                    int remap_outer, void* stream);
+
+/* Workspace (bytes) for the recurrent kernel's h exchange buffers + flags, for batch B, hidden H. */
+size_t onssen_blstm_rec_workspace_bytes(int B, int H);
+
+/* Persistent recurrent kernel for one layer, both directions.
+ *   gates [T*B][2*4Hp] fp32 pre-activations W_ih x + b (output of onssen_gemm_f16 with wih_p/bias_p)
+ *   whh_p packed recurrent weights (onssen_lstm_pack_layer)
+ *   y_h   [T*B][2*Hp] fp16 layer output (column dir*Hp + u), NULL to skip
+ *   y_f   [T*B][2*Hp] fp32 layer output, NULL to skip
+ *   dropout_p > 0: y_h/y_f are scaled by Bernoulli(1-p)/(1-p) (Philox, `seed`,`offset`); the recurrence
+ *                  itself uses the undropped h (PyTorch inter-layer dropout semantics)
+ *   use_tensor_cores: 1 = tcgen05 path (product), 0 = SIMT fp32-accumulate path (debug/validation)
+ * Returns ONSSEN_ERR_UNSUPPORTED if ceil(B / slices) > 32 for the slice count that fits the device;
+ * callers split the batch. */
+int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
+                         float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
+                         size_t workspace_bytes, int use_tensor_cores, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm1d over (B,T) per channel (replaces permute + nn.BatchNorm1d + permute,
+ * deep_clustering.py:36-38, enhancement.py:45-47).
+ * y [M][2Hp] fp32 (padded channel layout: channel j of 2H lives at (j/H)*Hp + j%H)
+ * training != 0: batch statistics (biased var for normalisation; running stats updated with momentum,
+ *                unbiased var), else running statistics.
+ * out_h [M][2Hp] fp16 = fp16(bn(y)) (pad columns zero) -- the A operand of the head GEMM.
+ * scratch: onssen_bn_scratch_bytes(M, H) bytes (per-chunk fp64 partial sums + folded scale/shift).
+ */
+int onssen_bn_num_chunks(int M);
+size_t onssen_bn_scratch_bytes(int M, int H);
+int onssen_bn_forward_f16(const float* y, int M, int H, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float eps, float momentum, int training,
+                          void* out_h, float* save_mean, float* save_invstd, void* scratch, void* stream);
+/* plain fp32 -> fp16 cast of an [M][2Hp] activation (models without BN, chimera.py) */
+int onssen_cast_f16(const float* y, long long n, void* out_h, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses
+ */
+/* Deep-clustering affinity loss (replaces loss_dc, onssen/loss/loss_dc.py:6-44 incl. its un-squared norms
+ * and (B,B) result): emb [B][N][D] fp32, label [B][N][S] (label_dtype), mag [B][N] fp32.
+ * loss_bb [B][B]: element [i][j] = sum_n mag[i][n] * l_j.  l [B] and mag_sum [B] are also written
+ * (either may be NULL). scratch: float[B * onssen_loss_dc_num_chunks(N) * (D*D + D*S + S*S + 1)] */
+int onssen_loss_dc_num_chunks(int N);
+int onssen_loss_dc_fwd(const float* emb, const void* label, int label_dtype, const float* mag, int B, int N,
+                       int D, int S, float* loss_bb, float* l, float* mag_sum, float* scratch, void* stream);
+
+/* PIT L1 mask-inference loss for two speakers (replaces the mask part of loss_chimera_msa/psa,
+ * onssen/loss/loss_chimera.py:25-29,53-57): per utterance
+ *   min( L1(mA*mix - t1) + L1(mB*mix - t2),  L1(mB*mix - t1) + L1(mA*mix - t2) )
+ * t_s = mag_s (cos_s == NULL, MSA) or min(mix, relu(mag_s*cos_s)) (PSA). mask strides allow the reference's
+ * strided views masks[...,0]/[...,1] (mask_stride = elements between consecutive (t,f) entries).
+ * out [B]; perm [B] int32 (0: A->s1, 1: swapped) may be NULL. */
+int onssen_loss_pit_l1_fwd(const float* mask_a, const float* mask_b, long long mask_stride, const float* mag_mix,
+                           const float* mag_s1, const float* mag_s2, const float* cos_s1, const float* cos_s2,
+                           int B, int N, float* out, int32_t* perm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONSSEN_B200_H_ */

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Build libonssen_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+OUT=../libonssen_b200.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
+mkdir -p build
+pids=()
+for f in capi gemm_tc05 lstm_rec pack loss stft; do
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ tc05.cuh -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ ../../include/onssen_b200.h -nt build/$f.o ]; then
+    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o build/$f.o &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -shared -o $OUT build/capi.o build/gemm_tc05.o build/lstm_rec.o build/pack.o build/loss.o build/stft.o -lcudart
+echo "built $OUT"

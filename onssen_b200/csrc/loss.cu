@@ -1,0 +1,377 @@
+// Loss reductions of the STFT-mask separation path.
+//
+// loss_dc (onssen/loss/loss_dc.py:6-44): with a_n = (sum_k y_nk) * e_n and per-point weight
+// w_n^2 = m_n / sum(m), the reference forms three weighted Gram matrices by bmm and takes UN-squared
+// Frobenius norms:  l = ||A^T A|| - 2||A^T Y|| + ||Y^T Y||, returned as the (B,B) outer product sum(m)_i*l_j.
+// Here one streaming pass over the embedding accumulates sum_n m_n a a^T (DxD), sum_n m_n a y^T (DxS),
+// sum_n m_n y y^T (SxS) and sum_n m_n in registers (the 1/sum(m) factor is linear and applied at the end),
+// so the 264 MB embedding of BASELINE cfg2 is read exactly once.  fp32 FMA on CUDA cores: at D=40 the
+// kernel sits at the fp32/HBM ridge (20 flop/B), tensor cores would need tf32 rounding of the parity-critical
+// loss operand, see DESIGN.md section 6.
+//
+// PIT L1 mask loss (onssen/loss/loss_chimera.py:25-29,53-57): four per-utterance L1 sums, min over the
+// two speaker permutations.
+#include "common.cuh"
+
+namespace onssen {
+namespace {
+
+constexpr int DC_THREADS = 256;
+constexpr int DC_PTS_PER_CHUNK = 1024;
+
+template <typename LT>
+__device__ __forceinline__ float lab_to_f(LT v) { return (float)v; }
+
+// ---- fast path: S == 2, D = TS * TG with TG*TG | 256 ----
+template <int D, int TS, typename LT>
+__global__ void __launch_bounds__(DC_THREADS)
+loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ label,
+                       const float* __restrict__ mag, int N, float* __restrict__ scratch) {
+  constexpr int TG = D / TS;
+  constexpr int GT = TG * TG;
+  constexpr int NG = DC_THREADS / GT;
+  constexpr int P = NG > 64 ? NG : 64;
+  constexpr int R = D * D + D * 2 + 4;
+  static_assert(TG * TS == D && NG * GT == DC_THREADS, "unsupported D");
+  extern __shared__ __align__(16) float sm[];
+  float* a_s = sm;                 // [P][D]   s_n * e_n
+  float* ma_s = a_s + P * D;       // [P][D]   m_n * s_n * e_n
+  float* y_s = ma_s + P * D;       // [P][2]
+  float* m_s = y_s + P * 2;        // [P]
+  float* red = sm;                 // reused after the main loop: [NG][R]
+
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int nchunk = gridDim.x;
+  const int n_begin = chunk * DC_PTS_PER_CHUNK;
+  const int n_end = min(N, n_begin + DC_PTS_PER_CHUNK);
+  const int tid = threadIdx.x;
+  const int g = tid / GT;
+  const int lt = tid % GT;
+  const int ti = lt / TG;
+  const int tj = lt % TG;
+
+  float acc[TS][TS];
+  float accy[TS][2];
+  float accs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < TS; ++i) {
+    accy[i][0] = accy[i][1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TS; ++j) acc[i][j] = 0.f;
+  }
+  const float* eb = emb + (long long)b * N * D;
+  const LT* lb = label + (long long)b * N * 2;
+  const float* mb = mag + (long long)b * N;
+
+  for (int n0 = n_begin; n0 < n_end; n0 += P) {
+    const int np = min(P, n_end - n0);
+    for (int i = tid; i < np; i += DC_THREADS) {
+      y_s[2 * i] = lab_to_f(lb[2 * (long long)(n0 + i)]);
+      y_s[2 * i + 1] = lab_to_f(lb[2 * (long long)(n0 + i) + 1]);
+      m_s[i] = mb[n0 + i];
+    }
+    __syncthreads();
+    for (int i = tid; i < np * D / 4; i += DC_THREADS) {
+      const int pnt = (i * 4) / D;
+      const float4 e = reinterpret_cast<const float4*>(eb + (long long)n0 * D)[i];
+      const float s = y_s[2 * pnt] + y_s[2 * pnt + 1];
+      reinterpret_cast<float4*>(a_s)[i] = make_float4(e.x * s, e.y * s, e.z * s, e.w * s);
+      // m * (s*e): keep the reference's association (mask first, then weight)
+      reinterpret_cast<float4*>(ma_s)[i] = make_float4(e.x * s * m_s[pnt], e.y * s * m_s[pnt],
+                                                       e.z * s * m_s[pnt], e.w * s * m_s[pnt]);
+    }
+    __syncthreads();
+    for (int pnt = g; pnt < np; pnt += NG) {
+      float rv[TS], cv[TS];
+#pragma unroll
+      for (int i = 0; i < TS; ++i) {
+        rv[i] = ma_s[pnt * D + ti * TS + i];
+        cv[i] = a_s[pnt * D + tj * TS + i];
+      }
+#pragma unroll
+      for (int i = 0; i < TS; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) acc[i][j] = fmaf(rv[i], cv[j], acc[i][j]);
+      if (tj == 0) {
+        const float y0 = y_s[2 * pnt], y1 = y_s[2 * pnt + 1];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+          accy[i][0] = fmaf(rv[i], y0, accy[i][0]);
+          accy[i][1] = fmaf(rv[i], y1, accy[i][1]);
+        }
+        if (ti == 0) {
+          const float m = m_s[pnt];
+          accs[0] = fmaf(m * y0, y0, accs[0]);
+          accs[1] = fmaf(m * y0, y1, accs[1]);
+          accs[2] = fmaf(m * y1, y1, accs[2]);
+          accs[3] += m;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // cross-group reduction in a fixed order (deterministic)
+  float* mine = red + g * R;
+#pragma unroll
+  for (int i = 0; i < TS; ++i)
+#pragma unroll
+    for (int j = 0; j < TS; ++j) mine[(ti * TS + i) * D + tj * TS + j] = acc[i][j];
+  if (tj == 0) {
+#pragma unroll
+    for (int i = 0; i < TS; ++i) {
+      mine[D * D + (ti * TS + i) * 2] = accy[i][0];
+      mine[D * D + (ti * TS + i) * 2 + 1] = accy[i][1];
+    }
+    if (ti == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mine[D * D + D * 2 + i] = accs[i];
+    }
+  }
+  __syncthreads();
+  float* out = scratch + ((long long)b * nchunk + chunk) * R;
+  for (int i = tid; i < R; i += DC_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) s += red[gg * R + i];
+    out[i] = s;
+  }
+}
+
+template <int D, int TS>
+constexpr size_t dc_smem_bytes() {
+  constexpr int TG = D / TS, GT = TG * TG, NG = DC_THREADS / GT, P = NG > 64 ? NG : 64;
+  constexpr size_t tile = (size_t)(2 * P * D + 3 * P) * 4;
+  constexpr size_t red = (size_t)NG * (D * D + D * 2 + 4) * 4;
+  return tile > red ? tile : red;
+}
+
+// ---- generic path: any D <= 128, S <= 4 (one thread per output entry, slow but exact same maths) ----
+template <typename LT>
+__global__ void __launch_bounds__(DC_THREADS)
+loss_dc_partial_generic(const float* __restrict__ emb, const LT* __restrict__ label,
+                        const float* __restrict__ mag, int N, int D, int S, float* __restrict__ scratch) {
+  constexpr int P = 32;
+  extern __shared__ __align__(16) float sm[];
+  float* a_s = sm;              // [P][D]
+  float* y_s = a_s + P * D;     // [P][S]
+  float* m_s = y_s + P * S;     // [P]
+  const int R = D * D + D * S + S * S + 1;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int n_begin = chunk * DC_PTS_PER_CHUNK;
+  const int n_end = min(N, n_begin + DC_PTS_PER_CHUNK);
+  const float* eb = emb + (long long)b * N * D;
+  const LT* lb = label + (long long)b * N * S;
+  const float* mb = mag + (long long)b * N;
+  float* out = scratch + ((long long)b * nchunk + chunk) * R;
+  for (int i = threadIdx.x; i < R; i += DC_THREADS) out[i] = 0.f;
+  for (int n0 = n_begin; n0 < n_end; n0 += P) {
+    const int np = min(P, n_end - n0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += DC_THREADS) {
+      float s = 0.f;
+      for (int k = 0; k < S; ++k) {
+        const float y = lab_to_f(lb[(long long)(n0 + i) * S + k]);
+        y_s[i * S + k] = y;
+        s += y;
+      }
+      m_s[i] = mb[n0 + i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * D; i += DC_THREADS) {
+      const int pnt = i / D;
+      float s = 0.f;
+      for (int k = 0; k < S; ++k) s += y_s[pnt * S + k];
+      a_s[i] = eb[(long long)n0 * D + i] * s;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < R; o += DC_THREADS) {
+      float accv = out[o];
+      if (o < D * D) {
+        const int i = o / D, j = o % D;
+        for (int pnt = 0; pnt < np; ++pnt) accv = fmaf(a_s[pnt * D + i] * m_s[pnt], a_s[pnt * D + j], accv);
+      } else if (o < D * D + D * S) {
+        const int i = (o - D * D) / S, k = (o - D * D) % S;
+        for (int pnt = 0; pnt < np; ++pnt) accv = fmaf(a_s[pnt * D + i] * m_s[pnt], y_s[pnt * S + k], accv);
+      } else if (o < D * D + D * S + S * S) {
+        const int k = (o - D * D - D * S) / S, l = (o - D * D - D * S) % S;
+        for (int pnt = 0; pnt < np; ++pnt) accv = fmaf(m_s[pnt] * y_s[pnt * S + k], y_s[pnt * S + l], accv);
+      } else {
+        for (int pnt = 0; pnt < np; ++pnt) accv += m_s[pnt];
+      }
+      out[o] = accv;
+    }
+  }
+}
+
+// per-utterance: ordered sum over chunks, norms, l_b and sum(m)_b
+__global__ void __launch_bounds__(256) loss_dc_final_kernel(const float* __restrict__ scratch, int nchunk, int D,
+                                                            int S, int fast_layout, float* __restrict__ l_out,
+                                                            float* __restrict__ msum_out) {
+  const int b = blockIdx.x;
+  // layout of one partial record
+  const int nG = D * D, nC = D * S;
+  const int nY = fast_layout ? 3 : S * S;
+  const int R = fast_layout ? (D * D + D * 2 + 4) : (D * D + D * S + S * S + 1);
+  __shared__ double s_part[3][8];
+  __shared__ float s_msum;
+  double q[3] = {0.0, 0.0, 0.0};
+  const float* base = scratch + (long long)b * nchunk * R;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    float v = 0.f;
+    for (int c = 0; c < nchunk; ++c) v += base[(long long)c * R + i];
+    if (i < nG) {
+      q[0] += (double)v * v;
+    } else if (i < nG + nC) {
+      q[1] += (double)v * v;
+    } else if (i < nG + nC + nY) {
+      double w = 1.0;
+      if (fast_layout && (i - nG - nC) == 1) w = 2.0;  // off-diagonal y0*y1 appears twice in Y^T Y
+      q[2] += w * (double)v * v;
+    } else {
+      s_msum = v;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < 3; ++k) {
+    const double r = warp_sum(q[k]);
+    if (lane == 0) s_part[k][warp] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < 3; ++k)
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t[k] += s_part[k][w];
+    const float msum = s_msum;
+    const float ne = sqrtf((float)t[0]) / msum;
+    const float ney = sqrtf((float)t[1]) / msum;
+    const float ny = sqrtf((float)t[2]) / msum;
+    const float l = ne - 2.0f * ney + ny;
+    if (l_out) l_out[b] = l;
+    if (msum_out) msum_out[b] = msum;
+  }
+}
+
+__global__ void loss_dc_outer_kernel(const float* __restrict__ l, const float* __restrict__ msum, int B,
+                                     float* __restrict__ loss_bb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * B) return;
+  const int i = idx / B, j = idx % B;
+  loss_bb[idx] = l[j] * msum[i];
+}
+
+template <int D, int TS, typename LT>
+int launch_dc_fast(const float* emb, const void* label, const float* mag, int B, int N, float* scratch,
+                   cudaStream_t s) {
+  constexpr size_t smem = dc_smem_bytes<D, TS>();
+  auto kern = loss_dc_partial_kernel<D, TS, LT>;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return ONSSEN_ERR_CUDA;
+  }
+  dim3 grid((N + DC_PTS_PER_CHUNK - 1) / DC_PTS_PER_CHUNK, B);
+  kern<<<grid, DC_THREADS, smem, s>>>(emb, (const LT*)label, mag, N, scratch);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+template <typename LT>
+int dispatch_dc(const float* emb, const void* label, const float* mag, int B, int N, int D, int S,
+                float* scratch, cudaStream_t s, int* fast) {
+  *fast = 1;
+  if (S == 2 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0) {
+    switch (D) {
+      case 20: return launch_dc_fast<20, 5, LT>(emb, label, mag, B, N, scratch, s);
+      case 40: return launch_dc_fast<40, 5, LT>(emb, label, mag, B, N, scratch, s);
+      case 8: return launch_dc_fast<8, 4, LT>(emb, label, mag, B, N, scratch, s);
+      case 16: return launch_dc_fast<16, 4, LT>(emb, label, mag, B, N, scratch, s);
+      case 32: return launch_dc_fast<32, 4, LT>(emb, label, mag, B, N, scratch, s);
+      case 64: return launch_dc_fast<64, 4, LT>(emb, label, mag, B, N, scratch, s);
+      default: break;
+    }
+  }
+  *fast = 0;
+  if (D > 128 || S > 4) return ONSSEN_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(32 * D + 32 * S + 32) * 4;
+  dim3 grid((N + DC_PTS_PER_CHUNK - 1) / DC_PTS_PER_CHUNK, B);
+  loss_dc_partial_generic<LT><<<grid, DC_THREADS, smem, s>>>(emb, (const LT*)label, mag, N, D, S, scratch);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- PIT L1
+__global__ void __launch_bounds__(1024)
+pit_l1_kernel(const float* __restrict__ mask_a, const float* __restrict__ mask_b, long long mstride,
+              const float* __restrict__ mix, const float* __restrict__ s1, const float* __restrict__ s2,
+              const float* __restrict__ c1, const float* __restrict__ c2, int N, float* __restrict__ out,
+              int32_t* __restrict__ perm) {
+  const int b = blockIdx.x;
+  const long long off = (long long)b * N;
+  double q[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float m = mix[off + n];
+    float t1 = s1[off + n], t2 = s2[off + n];
+    if (c1 != nullptr) {
+      t1 = fminf(m, fmaxf(t1 * c1[off + n], 0.f));
+      t2 = fminf(m, fmaxf(t2 * c2[off + n], 0.f));
+    }
+    const float ea = mask_a[(off + n) * mstride] * m;
+    const float eb = mask_b[(off + n) * mstride] * m;
+    q[0] += fabsf(ea - t1);
+    q[1] += fabsf(eb - t2);
+    q[2] += fabsf(eb - t1);
+    q[3] += fabsf(ea - t2);
+  }
+  __shared__ double sp[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < 4; ++k) {
+    const double r = warp_sum(q[k]);
+    if (lane == 0) sp[k][warp] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < 4; ++k)
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t[k] += sp[k][w];
+    const float l1 = (float)t[0] + (float)t[1];
+    const float l2 = (float)t[2] + (float)t[3];
+    out[b] = fminf(l1, l2);
+    if (perm) perm[b] = (l1 < l2) ? 0 : 1;   // loss_phase.py:21 uses strict <
+  }
+}
+
+}  // namespace
+}  // namespace onssen
+
+using namespace onssen;
+
+extern "C" int onssen_loss_dc_num_chunks(int N) { return (N + DC_PTS_PER_CHUNK - 1) / DC_PTS_PER_CHUNK; }
+
+extern "C" int onssen_loss_dc_fwd(const float* emb, const void* label, int label_dtype, const float* mag, int B,
+                                  int N, int D, int S, float* loss_bb, float* l, float* mag_sum, float* scratch,
+                                  void* stream) {
+  if (!emb || !label || !mag || !scratch || B <= 0 || N <= 0 || D <= 0 || S <= 0) return ONSSEN_ERR_ARG;
+  if (!l || !mag_sum) return ONSSEN_ERR_ARG;  // needed as intermediates for the (B,B) product
+  cudaStream_t s = (cudaStream_t)stream;
+  int fast = 0, rc;
+  switch (label_dtype) {
+    case ONSSEN_DT_F32: rc = dispatch_dc<float>(emb, label, mag, B, N, D, S, scratch, s, &fast); break;
+    case ONSSEN_DT_F64: rc = dispatch_dc<double>(emb, label, mag, B, N, D, S, scratch, s, &fast); break;
+    case ONSSEN_DT_U8: rc = dispatch_dc<uint8_t>(emb, label, mag, B, N, D, S, scratch, s, &fast); break;
+    default: return ONSSEN_ERR_ARG;
+  }
+  if (rc != ONSSEN_OK) return rc;
+  loss_dc_final_kernel<<<B, 256, 0, s>>>(scratch, onssen_loss_dc_num_chunks(N), D, S, fast, l, mag_sum);
+  if (loss_bb) loss_dc_outer_kernel<<<(B * B + 255) / 256, 256, 0, s>>>(l, mag_sum, B, loss_bb);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_loss_pit_l1_fwd(const float* mask_a, const float* mask_b, long long mask_stride,
+                                      const float* mag_mix, const float* mag_s1, const float* mag_s2,
+                                      const float* cos_s1, const float* cos_s2, int B, int N, float* out,
+                                      int32_t* perm, void* stream) {
+  if (!mask_a || !mask_b || !mag_mix || !mag_s1 || !mag_s2 || !out || B <= 0 || N <= 0 || mask_stride <= 0)
+    return ONSSEN_ERR_ARG;
+  if ((cos_s1 == nullptr) != (cos_s2 == nullptr)) return ONSSEN_ERR_ARG;
+  pit_l1_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(mask_a, mask_b, mask_stride, mag_mix, mag_s1, mag_s2,
+                                                      cos_s1, cos_s2, N, out, perm);
+  return ONSSEN_CHECK_LAUNCH();
+}

@@ -1,0 +1,110 @@
+"""Oracle vs the reference's own outputs (golden fixtures) and vs torch.stft -- CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import onssen_oracle as O
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_oracle_deep_clustering_matches_reference(name):
+    p, g = load_golden(f"dc_{name}.npz")
+    B, T, F, H, L, D = g["cfg"]
+    emb, = O.deep_clustering_forward(p, [g["feature"]], L, training=False)
+    np.testing.assert_allclose(emb, g["emb_eval"], atol=2e-5)
+    loss = O.loss_dc([emb], [g["one_hot"], g["mag_mix"]])
+    assert loss.shape == (B, B)
+    np.testing.assert_allclose(loss, g["loss_eval"], rtol=2e-5)
+    emb_t, = O.deep_clustering_forward(p, [g["feature"]], L, training=True)
+    np.testing.assert_allclose(emb_t, g["emb_train"], atol=2e-5)
+    np.testing.assert_allclose(O.loss_dc([emb_t], [g["one_hot"], g["mag_mix"]]), g["loss_train"], rtol=2e-5)
+    # running statistics update (momentum 0.1, unbiased variance)
+    y = O.blstm_stack(g["feature"], p, "rnn.", L)
+    _, rm, rv = O.batchnorm_bt(y, p, "bn.", True)
+    np.testing.assert_allclose(rm, g["bn_rm_after"], atol=1e-6)
+    np.testing.assert_allclose(rv, g["bn_rv_after"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_oracle_chimera_matches_reference(name):
+    p, g = load_golden(f"chimera_{name}.npz")
+    L = g["cfg"][4]
+    e, ma, mb = O.chimera_forward(p, [g["feature"]], L)
+    np.testing.assert_allclose(e, g["emb"], atol=2e-5)
+    np.testing.assert_allclose(ma, g["mask_a"], atol=2e-6)
+    np.testing.assert_allclose(mb, g["mask_b"], atol=2e-6)
+    lab4 = [g["one_hot"], g["mag_mix"], g["mag_s1"], g["mag_s2"]]
+    np.testing.assert_allclose(O.loss_chimera_msa([e, ma, mb], lab4), g["loss_msa"], rtol=2e-5)
+    np.testing.assert_allclose(O.loss_chimera_psa([e, ma, mb], lab4 + [g["cos_s1"], g["cos_s2"]]), g["loss_psa"],
+                               rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_oracle_enhance_matches_reference(name):
+    p, g = load_golden(f"enhance_{name}.npz")
+    L = g["cfg"][4]
+    c_eval, = O.enhance_forward(p, [g["feature"], g["mag_noisy"]], L, training=False)
+    np.testing.assert_allclose(c_eval, g["clean_eval"], atol=2e-5)
+    c_tr, = O.enhance_forward(p, [g["feature"], g["mag_noisy"]], L, training=True)
+    np.testing.assert_allclose(c_tr, g["clean_train"], atol=2e-5)
+    np.testing.assert_allclose(O.loss_mask_msa([c_eval], [g["mag_clean"], g["cos_diff"]]), g["loss_msa"], rtol=1e-5)
+    sig = 1 / (1 + np.exp(-c_eval))
+    np.testing.assert_allclose(O.loss_mask_psa([sig], [g["mag_noisy"], g["mag_clean"], g["cos_diff"]]),
+                               g["loss_psa"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n_fft,hop,ns", [(256, 64, 32000), (512, 128, 64000), (1024, 256, 64000), (64, 16, 1000)])
+def test_oracle_stft_matches_torch(n_fft, hop, ns):
+    mix, _, _ = O.synth_utterance(3, ns)
+    spec = O.stft(mix, n_fft, hop)
+    assert spec.shape == (1 + ns // hop, n_fft // 2 + 1) and spec.dtype == np.complex64
+    ref = torch.stft(torch.from_numpy(mix), n_fft, hop, window=torch.hann_window(n_fft, periodic=True), center=True,
+                     pad_mode="reflect", return_complex=True).T.numpy()
+    scale = np.abs(ref).max()
+    assert np.abs(spec - ref).max() <= 2e-6 * scale
+    # istft round trip (window-sum-square normalisation) and agreement with torch.istft
+    y = O.istft(spec, hop, ns)
+    assert np.abs(y - mix).max() <= 1e-5 * np.abs(mix).max() + 1e-7
+    yt = torch.istft(torch.from_numpy(spec.T.copy()), n_fft, hop, window=torch.hann_window(n_fft, periodic=True),
+                     center=True, length=ns).numpy()
+    assert np.abs(y - yt).max() <= 1e-5 * np.abs(mix).max() + 1e-7
+
+
+def test_oracle_frame_indexing_and_labels():
+    # 4 s @ 8 kHz -> 501 frames, crop start exclusive bound 101 (np.random.randint(frames - T))
+    assert O.num_crop_starts(32000, 64, 400) == 101
+    # 16 kHz, n_fft 1024 / hop 256: 251 frames <= 400 -> tiled x2 = 502 -> bound 102
+    assert O.num_crop_starts(64000, 256, 400) == 102
+    spec = (np.arange(5 * 3).reshape(5, 3) + 0j).astype(np.complex64)
+    tiled = O.tile_and_crop(spec, 7, 2)           # 5 <= 7 -> times = 2 -> 10 frames, rows 2..8
+    np.testing.assert_array_equal(tiled[:, 0].real, (np.arange(2, 9) % 5) * 3)
+    # labels: ties -> speaker 0, strict < for the VAD
+    feat = np.array([[0.0, -1.0, -2.0, -2.0000002]], dtype=np.float32)
+    m1 = np.array([[1.0, 2.0, 3.0, 1.0]], dtype=np.float32)
+    m2 = np.array([[1.0, 3.0, 1.0, 5.0]], dtype=np.float32)
+    oh = O.one_hot(feat, m1, m2, 40)
+    np.testing.assert_array_equal(oh[0], [[1, 0], [0, 1], [1, 0], [0, 0]])
+    assert oh.dtype == np.float64
+
+
+def test_oracle_featurize_layouts():
+    mix, s1, s2 = O.synth_utterance(0, 8000)
+    for name, nin, nlab in [("dc", 1, 2), ("chimera", 1, 4), ("chimera++", 1, 6), ("phase", 2, 6)]:
+        inp, lab = O.featurize(mix, s1, s2, 256, 64, 100, 5, 40, name)
+        assert len(inp) == nin and len(lab) == nlab
+        assert inp[0].shape == (100, 129) and lab[0].shape == (100, 129, 2)
+    active = lab[0].sum(-1).mean()
+    assert 0.2 < active < 0.98           # the synthetic mixtures do exercise the VAD
+
+
+def test_oracle_loss_phase_repaired_runs():
+    rng = np.random.RandomState(0)
+    B, T, F, D = 2, 6, 5, 4
+    emb = O.l2_normalize(rng.standard_normal((B, T, F, D)).astype(np.float32))
+    ma = rng.uniform(size=(B, T, F)).astype(np.float32)
+    ph = lambda: O.l2_normalize(rng.standard_normal((B, T, F, 2)).astype(np.float32))
+    mags = [np.abs(rng.standard_normal((B, T, F))).astype(np.float32) for _ in range(3)]
+    oh = np.zeros((B, T, F, 2)); oh[..., 0] = 1
+    out = O.loss_phase([emb, ma, 1 - ma, ph(), ph()], [oh, mags[0], mags[1], mags[2], ph(), ph()])
+    assert out.shape == (B, B) and np.isfinite(out).all()
