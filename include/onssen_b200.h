@@ -102,6 +102,12 @@ int onssen_lstm_pack_layer(const float* w_ih_f, const float* w_hh_f, const float
                            int H, int I, int in_is_blstm, int Hin, void* wih_p, void* whh_p, float* bias_p,
                            void* stream);
 
+/* Linear weight w [N][K] fp32 -> out [N][Kp] fp16 (zero padded). in_is_blstm: K == 2*Hin and input j maps
+ * to column (j/Hin)*Hinp + j%Hin (Kp = 2*Hinp) -- the padded channel layout of the BLSTM outputs; else
+ * Kp >= K, multiple of 8 (use 64*ceil(K/64)). (fc_dc / fc_mi / fc_pre / fc_post of the reference models) */
+int onssen_pack_linear_f16(const float* w, int N, int K, int in_is_blstm, int Hin, void* out, int Kp,
+                           void* stream);
+
 /* fp16 tensor-core GEMM with fused epilogue: out = epi(A[M][K] * W[N][K]^T + bias).
  * epi: 0 none, 1 sigmoid, 2 relu, 3 L2-normalise consecutive groups of `group` columns
  * (F.normalize eps 1e-12, deep_clustering.py:41). remap_inner>0: time-major row m=t*B+b (inner=B,outer=T)

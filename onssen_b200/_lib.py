@@ -1,0 +1,310 @@
+"""ctypes binding of libonssen_b200.so (the C ABI declared in include/onssen_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+PyTorch is used only as the owner of device memory / streams; every function here takes torch CUDA
+tensors, passes raw device pointers + the current CUDA stream, and checks the integer status.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libonssen_b200.so")
+
+DT_F32, DT_F64, DT_U8 = 0, 1, 2
+_DT = {torch.float32: DT_F32, torch.float64: DT_F64, torch.uint8: DT_U8}
+
+c_int, c_ll, c_vp, c_sz, c_f, c_ull = (ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_size_t,
+                                       ctypes.c_float, ctypes.c_ulonglong)
+
+# name -> (restype, argtypes); mirrors include/onssen_b200.h one to one
+_SIGNATURES = {
+    "onssen_version": (ctypes.c_char_p, []),
+    "onssen_error_string": (ctypes.c_char_p, [c_int]),
+    "onssen_num_sms": (c_int, []),
+    "onssen_stft_features": (c_int, [c_vp] * 3 + [c_int] * 4 + [c_vp, c_int] + [c_vp] * 10 + [c_vp]),
+    "onssen_one_hot_vad": (c_int, [c_vp] * 4 + [c_f, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "onssen_istft_scratch_bytes": (c_sz, [c_int] * 4),
+    "onssen_istft_masked": (c_int, [c_vp] * 3 + [c_int] * 6 + [c_vp, c_vp, c_vp]),
+    "onssen_pack_input_f16": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "onssen_lstm_pack_layer": (c_int, [c_vp] * 8 + [c_int] * 4 + [c_vp] * 4),
+    "onssen_pack_linear_f16": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "onssen_gemm_l2norm_supported": (c_int, [c_int]),
+    "onssen_gemm_f16": (c_int, [c_vp] * 4 + [c_int] * 3 + [c_ll] * 3 + [c_int] * 4 + [c_vp]),
+    "onssen_blstm_rec_workspace_bytes": (c_sz, [c_int, c_int]),
+    "onssen_blstm_rec_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_f, c_ull, c_ull, c_vp, c_sz,
+                                     c_int, c_vp]),
+    "onssen_bn_num_chunks": (c_int, [c_int]),
+    "onssen_bn_scratch_bytes": (c_sz, [c_int, c_int]),
+    "onssen_bn_forward_f16": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_int, c_vp, c_vp, c_vp,
+                                      c_vp, c_vp]),
+    "onssen_cast_f16": (c_int, [c_vp, c_ll, c_vp, c_vp]),
+    "onssen_loss_dc_num_chunks": (c_int, [c_int]),
+    "onssen_loss_dc_fwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp]),
+    "onssen_loss_pit_l1_fwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 5 + [c_int, c_int, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+# bookkeeping for bench.py: number of kernels launched through this binding, and optional CUDA-event pairs
+# around the recurrent kernel launches (set REC_EVENTS to a list to collect them)
+LAUNCHES = [0]
+REC_EVENTS = None
+_KERNELS_PER_CALL = {"onssen_stft_features": 2, "onssen_one_hot_vad": 1, "onssen_istft_masked": 2,
+                     "onssen_pack_input_f16": 1, "onssen_lstm_pack_layer": 3, "onssen_pack_linear_f16": 1,
+                     "onssen_gemm_f16": 1, "onssen_blstm_rec_fwd": 1, "onssen_bn_forward_f16": 3,
+                     "onssen_cast_f16": 1, "onssen_loss_dc_fwd": 3, "onssen_loss_pit_l1_fwd": 1}
+
+
+class OnssenB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OnssenB200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(onssen_b200 has no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def _check(rc, what):
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 0)
+    if rc != 0:
+        msg = load().onssen_error_string(rc).decode()
+        detail = ""
+        if rc == -3 and torch.cuda.is_available():
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:  # surface the sticky CUDA error text
+                detail = f" ({e})"
+        raise OnssenB200Error(f"{what} failed: {msg} [{rc}]{detail}")
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise OnssenB200Error(f"{name} must be a CUDA tensor (onssen_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise OnssenB200Error(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise OnssenB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def num_sms():
+    return load().onssen_num_sms()
+
+
+def hp_of(H):
+    return (H + 31) // 32 * 32
+
+
+# ------------------------------------------------------------------------------------------------ featurizer
+def stft_features(wav_mix, wav_s1, wav_s2, n_fft, hop, crop_start, T, want):
+    """want: iterable of output names among feature, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2, ph_mix, ph_s1,
+    ph_s2, feat_max. Returns dict name -> tensor."""
+    lib = load()
+    _req(wav_mix, torch.float32, "wav_mix")
+    B, ns = wav_mix.shape
+    F = n_fft // 2 + 1
+    dev = wav_mix.device
+    out = {}
+    for k in want:
+        if k == "feat_max":
+            out[k] = torch.empty(B, device=dev, dtype=torch.float32)
+        elif k.startswith("ph_"):
+            out[k] = torch.empty(B, T, F, 2, device=dev, dtype=torch.float32)
+        else:
+            out[k] = torch.empty(B, T, F, device=dev, dtype=torch.float32)
+    g = out.get
+    crop_start = _req(crop_start.to(device=dev, dtype=torch.int32), torch.int32, "crop_start")
+    if wav_s1 is not None:
+        _req(wav_s1, torch.float32, "wav_s1"); _req(wav_s2, torch.float32, "wav_s2")
+    rc = lib.onssen_stft_features(_p(wav_mix), _p(wav_s1), _p(wav_s2), B, ns, n_fft, hop, _p(crop_start), T,
+                                  _p(g("feature")), _p(g("mag_mix")), _p(g("mag_s1")), _p(g("mag_s2")),
+                                  _p(g("cos_s1")), _p(g("cos_s2")), _p(g("ph_mix")), _p(g("ph_s1")), _p(g("ph_s2")),
+                                  _p(g("feat_max")), _stream())
+    _check(rc, "onssen_stft_features")
+    return out
+
+
+def one_hot_vad(feature, mag_s1, mag_s2, feat_max, db_threshold, dtype=torch.float32):
+    lib = load()
+    B, T, F = feature.shape
+    out = torch.empty(B, T, F, 2, device=feature.device, dtype=dtype)
+    rc = lib.onssen_one_hot_vad(_p(_req(feature, torch.float32)), _p(_req(mag_s1, torch.float32)),
+                                _p(_req(mag_s2, torch.float32)), _p(_req(feat_max, torch.float32)),
+                                float(db_threshold), B, T, F, _p(out), _DT[dtype], _stream())
+    _check(rc, "onssen_one_hot_vad")
+    return out
+
+
+def istft_masked(stft_re, stft_im, mask, n_fft, hop, nsample):
+    lib = load()
+    B, frames, F = stft_re.shape
+    assert F == n_fft // 2 + 1
+    S = 1 if mask is None else mask.shape[1]
+    out = torch.empty(B, S, nsample, device=stft_re.device, dtype=torch.float32)
+    scratch = torch.empty(lib.onssen_istft_scratch_bytes(B, S, frames, n_fft) // 4, device=stft_re.device,
+                          dtype=torch.float32)
+    rc = lib.onssen_istft_masked(_p(_req(stft_re, torch.float32)), _p(_req(stft_im, torch.float32)),
+                                 _p(None if mask is None else _req(mask, torch.float32)), B, S, frames, n_fft, hop,
+                                 nsample, _p(out), _p(scratch), _stream())
+    _check(rc, "onssen_istft_masked")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ BLSTM pieces
+def pack_input_f16(x):
+    lib = load()
+    B, T, I = x.shape
+    Kp = (I + 63) // 64 * 64
+    xh = torch.empty(T * B, Kp, device=x.device, dtype=torch.float16)
+    _check(lib.onssen_pack_input_f16(_p(_req(x, torch.float32, "x")), B, T, I, _p(xh), Kp, _stream()),
+           "onssen_pack_input_f16")
+    return xh
+
+
+def lstm_pack_layer(wf, wr, H, I, in_is_blstm, Hin):
+    """wf / wr: (w_ih, w_hh, b_ih, b_hh) fp32 CUDA tensors for the forward / reverse direction."""
+    lib = load()
+    Hp = hp_of(H)
+    Kp = 2 * hp_of(Hin) if in_is_blstm else (I + 63) // 64 * 64
+    dev = wf[0].device
+    wih_p = torch.empty(2 * 4 * Hp, Kp, device=dev, dtype=torch.float16)
+    whh_p = torch.empty(2 * 4 * Hp * Hp, device=dev, dtype=torch.float16)
+    bias_p = torch.empty(2 * 4 * Hp, device=dev, dtype=torch.float32)
+    args = [_p(_req(t.detach(), torch.float32, "lstm weight")) for t in list(wf) + list(wr)]
+    rc = lib.onssen_lstm_pack_layer(*args, H, I, int(in_is_blstm), Hin, _p(wih_p), _p(whh_p), _p(bias_p), _stream())
+    _check(rc, "onssen_lstm_pack_layer")
+    return wih_p, whh_p, bias_p
+
+
+def pack_linear_f16(w, in_is_blstm, Hin=0):
+    lib = load()
+    N, K = w.shape
+    Kp = 2 * hp_of(Hin) if in_is_blstm else (K + 63) // 64 * 64
+    out = torch.empty(N, Kp, device=w.device, dtype=torch.float16)
+    rc = lib.onssen_pack_linear_f16(_p(_req(w.detach(), torch.float32, "weight")), N, K, int(in_is_blstm), Hin,
+                                    _p(out), Kp, _stream())
+    _check(rc, "onssen_pack_linear_f16")
+    return out
+
+
+def gemm_f16(A, W, bias, out, M, N, K, ld_out, epi=0, group=0, remap_inner=0, remap_outer=0):
+    lib = load()
+    _req(A, torch.float16, "A"); _req(W, torch.float16, "W"); _req(out, torch.float32, "out")
+    rc = lib.onssen_gemm_f16(_p(A), _p(W), _p(bias), _p(out), M, N, K, A.stride(0), W.stride(0), ld_out, epi, group,
+                             remap_inner, remap_outer, _stream())
+    _check(rc, "onssen_gemm_f16")
+    return out
+
+
+def gemm_l2norm_supported(group):
+    return bool(load().onssen_gemm_l2norm_supported(group))
+
+
+def blstm_rec_workspace(B, H, device):
+    n = load().onssen_blstm_rec_workspace_bytes(B, H)
+    return torch.empty(n, device=device, dtype=torch.uint8)
+
+
+def blstm_rec_fwd(gates, whh_p, B, T, H, y_h=None, y_f=None, dropout_p=0.0, seed=0, offset=0, workspace=None,
+                  use_tensor_cores=True):
+    lib = load()
+    if workspace is None:
+        workspace = blstm_rec_workspace(B, H, gates.device)
+    ev = None
+    if REC_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    rc = lib.onssen_blstm_rec_fwd(_p(_req(gates, torch.float32, "gates")), _p(whh_p), B, T, H, _p(y_h), _p(y_f),
+                                  float(dropout_p), int(seed), int(offset), _p(workspace), workspace.numel(),
+                                  int(use_tensor_cores), _stream())
+    if ev is not None:
+        ev[1].record()
+        REC_EVENTS.append(ev)
+    _check(rc, "onssen_blstm_rec_fwd")
+
+
+def bn_forward_f16(y, M, H, gamma, beta, running_mean, running_var, eps, momentum, training, save_stats=False):
+    lib = load()
+    Hp = hp_of(H)
+    out_h = torch.empty(M, 2 * Hp, device=y.device, dtype=torch.float16)
+    scratch = torch.empty(lib.onssen_bn_scratch_bytes(M, H), device=y.device, dtype=torch.uint8)
+    sm = si = None
+    if save_stats:
+        sm = torch.empty(2 * H, device=y.device, dtype=torch.float32)
+        si = torch.empty(2 * H, device=y.device, dtype=torch.float32)
+    rc = lib.onssen_bn_forward_f16(_p(_req(y, torch.float32, "y")), M, H, _p(gamma), _p(beta), _p(running_mean),
+                                   _p(running_var), float(eps), float(momentum), int(training), _p(out_h), _p(sm),
+                                   _p(si), _p(scratch), _stream())
+    _check(rc, "onssen_bn_forward_f16")
+    return out_h, sm, si
+
+
+def cast_f16(y):
+    lib = load()
+    out = torch.empty(y.shape, device=y.device, dtype=torch.float16)
+    _check(lib.onssen_cast_f16(_p(_req(y, torch.float32, "y")), y.numel(), _p(out), _stream()), "onssen_cast_f16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def loss_dc_fwd(emb, label, mag):
+    """emb (B,N,D) fp32, label (B,N,S) f32/f64/u8, mag (B,N) fp32 -> (loss_bb (B,B), l (B,), mag_sum (B,))"""
+    lib = load()
+    B, N, D = emb.shape
+    S = label.shape[-1]
+    if label.dtype not in _DT:
+        label = label.float()
+    dev = emb.device
+    loss_bb = torch.empty(B, B, device=dev, dtype=torch.float32)
+    l = torch.empty(B, device=dev, dtype=torch.float32)
+    msum = torch.empty(B, device=dev, dtype=torch.float32)
+    nchunk = lib.onssen_loss_dc_num_chunks(N)
+    scratch = torch.empty(B * nchunk * (D * D + D * S + S * S + 4), device=dev, dtype=torch.float32)
+    rc = lib.onssen_loss_dc_fwd(_p(_req(emb, torch.float32, "embedding")), _p(_req(label, None, "label")),
+                                _DT[label.dtype], _p(_req(mag, torch.float32, "mag_mix")), B, N, D, S, _p(loss_bb),
+                                _p(l), _p(msum), _p(scratch), _stream())
+    _check(rc, "onssen_loss_dc_fwd")
+    return loss_bb, l, msum
+
+
+def loss_pit_l1_fwd(mask_a, mask_b, mask_stride, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None):
+    lib = load()
+    B = mag_mix.shape[0]
+    N = mag_mix.numel() // B
+    out = torch.empty(B, device=mag_mix.device, dtype=torch.float32)
+    perm = torch.empty(B, device=mag_mix.device, dtype=torch.int32)
+    rc = lib.onssen_loss_pit_l1_fwd(_p(mask_a), _p(mask_b), mask_stride, _p(_req(mag_mix, torch.float32)),
+                                    _p(_req(mag_s1, torch.float32)), _p(_req(mag_s2, torch.float32)),
+                                    _p(None if cos_s1 is None else _req(cos_s1, torch.float32)),
+                                    _p(None if cos_s2 is None else _req(cos_s2, torch.float32)), B, N, _p(out),
+                                    _p(perm), _stream())
+    _check(rc, "onssen_loss_pit_l1_fwd")
+    return out, perm

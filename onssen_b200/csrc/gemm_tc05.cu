@@ -366,9 +366,12 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
   if (rc != ONSSEN_OK) return rc;
   if (epi == 3) {
     switch (group) {
+      case 4: return launch<4>(ta, tw, p, stream);
       case 8: return launch<8>(ta, tw, p, stream);
+      case 12: return launch<12>(ta, tw, p, stream);
       case 16: return launch<16>(ta, tw, p, stream);
       case 20: return launch<20>(ta, tw, p, stream);
+      case 24: return launch<24>(ta, tw, p, stream);
       case 32: return launch<32>(ta, tw, p, stream);
       case 40: return launch<40>(ta, tw, p, stream);
       default: return ONSSEN_ERR_UNSUPPORTED;
@@ -378,7 +381,8 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
 }
 
 bool gemm_l2norm_group_supported(int group) {
-  return group == 8 || group == 16 || group == 20 || group == 32 || group == 40;
+  return group == 4 || group == 8 || group == 12 || group == 16 || group == 20 || group == 24 || group == 32 ||
+         group == 40;
 }
 
 }  // namespace onssen

@@ -87,6 +87,25 @@ __global__ void pack_whh_kernel(PackArgs a, __half* __restrict__ out) {
   }
 }
 
+// Linear weight [N][K] fp32 -> fp16 [N][Kp]; blstm != 0 maps input j of 2*Hin to column (j/Hin)*Hinp + j%Hin
+__global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, int blstm, int Hin, int Hinp,
+                                   int Kp, __half* __restrict__ out) {
+  const long long total = (long long)N * Kp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kp);
+    const long long n = idx / Kp;
+    int j = -1;
+    if (blstm) {
+      const int din = k / Hinp, uin = k % Hinp;
+      if (din < 2 && uin < Hin) j = din * Hin + uin;
+    } else if (k < K) {
+      j = k;
+    }
+    out[idx] = to_half_sat(j >= 0 ? w[n * K + j] : 0.f);
+  }
+}
+
 __global__ void pack_bias_kernel(PackArgs a, float* __restrict__ out) {
   const int G4 = 4 * a.Hp;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,6 +271,15 @@ extern "C" int onssen_lstm_pack_layer(const float* w_ih_f, const float* w_hh_f, 
   const long long n_hh = 2LL * 4 * a.Hp * a.Hp;
   pack_whh_kernel<<<grid_for(n_hh, 256), 256, 0, s>>>(a, (__half*)whh_p);
   pack_bias_kernel<<<(2 * 4 * a.Hp + 255) / 256, 256, 0, s>>>(a, bias_p);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_pack_linear_f16(const float* w, int N, int K, int in_is_blstm, int Hin, void* out, int Kp,
+                                      void* stream) {
+  if (!w || !out || N <= 0 || K <= 0 || (Kp & 7)) return ONSSEN_ERR_ARG;
+  if (in_is_blstm ? (K != 2 * Hin || Kp != 2 * hp_of(Hin)) : (Kp < K)) return ONSSEN_ERR_ARG;
+  pack_linear_kernel<<<grid_for((long long)N * Kp, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, N, K, in_is_blstm, Hin, in_is_blstm ? hp_of(Hin) : 0, Kp, (__half*)out);
   return ONSSEN_CHECK_LAUNCH();
 }
 

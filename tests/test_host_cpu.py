@@ -1,0 +1,69 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/onssen_b200.h declares, the
+host mirror keeps the reference's plugin surface, and the product path fails loudly without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "onssen_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(onssen_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from onssen_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the extension first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/onssen_b200.h but not exported"
+    # the ctypes table binds exactly the declared surface
+    assert sorted(_lib.exported_symbols()) == declared
+    _lib.load()
+    assert b"sm_100a" in _lib.load().onssen_version()
+
+
+def test_plugin_surface_matches_reference_names():
+    import onssen_b200 as ob
+    m = ob.nn.deep_clustering(129, hidden_dim=600, num_layers=3, embedding_dim=20)
+    keys = [k for k in m.state_dict() if "num_batches" not in k]
+    for l in range(3):
+        for suf in ("", "_reverse"):
+            for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                assert f"rnn.{n}_l{l}{suf}" in keys
+    for k in ("bn.weight", "bn.bias", "bn.running_mean", "bn.running_var", "fc_dc.weight", "fc_dc.bias"):
+        assert k in keys
+    assert m.fc_dc.weight.shape == (129 * 20, 1200)
+    c = ob.nn.chimera(129, 300, 4, 20, num_speaker=2)
+    assert c.fc_mi.weight.shape == (258, 600) and "bn.weight" not in c.state_dict()
+    for fn in ("loss_dc", "loss_chimera_msa", "loss_chimera_psa"):
+        assert callable(getattr(ob.loss, fn))
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import onssen_b200 as ob
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = ob.nn.deep_clustering(9, 8, 1, 4).eval()
+    with torch.no_grad(), pytest.raises(ob._lib.OnssenB200Error):
+        m([torch.zeros(1, 4, 9)])
+    with pytest.raises(AssertionError):
+        m([torch.zeros(1, 4, 9), torch.zeros(1)])       # same arity assert as deep_clustering.py:31
+
+
+def test_attrdict_and_optimizer_shims():
+    import onssen_b200 as ob
+    a = ob.utils.AttrDict({"model_options": {"input_dim": 129}, "device": "cpu"})
+    assert a.model_options.input_dim == 129 and a["model_options"]["input_dim"] == 129
+    a.model = 3
+    assert a["model"] == 3 and "model" in a
+    p = [torch.nn.Parameter(torch.zeros(2))]
+    assert isinstance(ob.utils.build_optimizer(p, a.__class__({"name": "adam", "lr": 1e-3})), torch.optim.Adam)
+    assert ob.data.num_crop_starts(32000, 64, 400) == 101
