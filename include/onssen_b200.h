@@ -46,6 +46,8 @@ int onssen_num_sms(void);
  * onssen/data/wsj0_2mix.py:114-152, executed per batch on the device instead of per item on the host)
  *
  * wav_*      [B][nsample] float32 waveforms (mix, s1, s2); s1/s2 may be NULL when no label output needs them
+ * nsample_per_utt  optional [B] int32 true lengths (each n_fft/2 < len <= nsample, rows zero padded): lets a
+ *            batch hold utterances of different duration (frames, reflect padding and tiling per utterance)
  * crop_start [B] int32 first frame of the crop in the (possibly tiled) frame sequence
  *            (reference: np.random.randint(frames - T), wsj0_2mix.py:125) -- explicit so indexing is exact
  * n_fft in {64..2048, power of two}; frames = 1 + nsample/hop (center=True, reflect padding, periodic Hann);
@@ -61,7 +63,8 @@ int onssen_num_sms(void);
 int onssen_stft_features(const float* wav_mix, const float* wav_s1, const float* wav_s2, int B, int nsample,
                          int n_fft, int hop, const int32_t* crop_start, int T, float* feature, float* mag_mix,
                          float* mag_s1, float* mag_s2, float* cos_s1, float* cos_s2, float* ph_mix,
-                         float* ph_s1, float* ph_s2, float* feat_max, void* stream);
+                         float* ph_s1, float* ph_s2, float* feat_max, const int32_t* nsample_per_utt,
+                         void* stream);
 
 /* Ideal-binary labels + VAD  (replaces get_one_hot, feature_utils.py:83-95).
  * one_hot [B][T][F][2] written as out_dtype (ONSSEN_DT_*): argmax over (mag_s1, mag_s2) (ties -> 0),
@@ -93,8 +96,8 @@ int onssen_pack_input_f16(const float* x, int B, int T, int I, void* xh, int Kp,
  *                1 -> I == 2*Hin; input index j maps to column (j/Hin)*Hinp + j%Hin, Kp = 2*Hinp
  * Outputs:
  *   wih_p  [2*4Hp][Kp] fp16, row n = dir*4Hp + rb*128 + 4*ul + gate  <->  source row gate*H + rb*32 + ul
- *   whh_p  [2][Hp/32][Hp/8][128][8] fp16 (per (dir,row-block) a contiguous slab in the no-swizzle UMMA
- *          K-major core-matrix layout: [k/8][row][k%8]), same row permutation, zero padded
+ *   whh_p  [2][Hp/32][128][Hp] fp16 (per (dir,row-block) a contiguous row-major slab of the 128 permuted gate
+ *          rows; each row becomes one TMEM lane of the resident A operand), zero padded
  *   bias_p [2*4Hp] fp32 = b_ih + b_hh, same permutation
  */
 int onssen_lstm_pack_layer(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
@@ -134,6 +137,10 @@ int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B, int T, in
                          float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
                          size_t workspace_bytes, int use_tensor_cores, void* stream);
 
+/* Debug/profiling hook: when set to a device buffer of 64 int64, the next recurrent launches record clock64
+ * stamps of CTA 0 for steps 100..103 (16 slots per step; see REC_TRACE in csrc/lstm_rec.cu). NULL disables. */
+void onssen_blstm_rec_set_trace(void* device_buf_64_int64);
+
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm1d over (B,T) per channel (replaces permute + nn.BatchNorm1d + permute,
  * deep_clustering.py:36-38, enhancement.py:45-47).
@@ -157,7 +164,8 @@ int onssen_cast_f16(const float* y, long long n, void* out_h, void* stream);
 /* Deep-clustering affinity loss (replaces loss_dc, onssen/loss/loss_dc.py:6-44 incl. its un-squared norms
  * and (B,B) result): emb [B][N][D] fp32, label [B][N][S] (label_dtype), mag [B][N] fp32.
  * loss_bb [B][B]: element [i][j] = sum_n mag[i][n] * l_j.  l [B] and mag_sum [B] are also written
- * (either may be NULL). scratch: float[B * onssen_loss_dc_num_chunks(N) * (D*D + D*S + S*S + 1)] */
+ * (l and mag_sum are required as intermediates).
+ * scratch: float[B * (onssen_loss_dc_num_chunks(N) + 1) * (D*D + D*S + S*S + 4)] */
 int onssen_loss_dc_num_chunks(int N);
 int onssen_loss_dc_fwd(const float* emb, const void* label, int label_dtype, const float* mag, int B, int N,
                        int D, int S, float* loss_bb, float* l, float* mag_sum, float* scratch, void* stream);
@@ -171,6 +179,36 @@ int onssen_loss_dc_fwd(const float* emb, const void* label, int label_dtype, con
 int onssen_loss_pit_l1_fwd(const float* mask_a, const float* mask_b, long long mask_stride, const float* mag_mix,
                            const float* mag_s1, const float* mag_s2, const float* cos_s1, const float* cos_s2,
                            int B, int N, float* out, int32_t* perm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Enhancement / phase-network variants of the path
+ */
+/* out[m][k] = fp16(a[m][k] * b[m][k]) for k < F, zero padded to Kp: mask * relu(fc_pre(mag_noisy)), the fp16
+ * operand of fc_post (onssen/nn/enhancement.py:49-50). a, b [M][F] fp32. */
+int onssen_mul_pack_f16(const float* a, const float* b, long long M, int F, void* out, int Kp, void* stream);
+
+/* Second-BLSTM input of phase_net (onssen/nn/phase_network.py:46-49,56): time-major fp16 rows
+ * [ x_mag*mask (F) | x_phase viewed (2F) | 0 pad ]; x_mag [B][T][F], mask element (b,t,f) at
+ * mask[((b*T+t)*F+f)*mask_stride], x_phase [B][T][F][2]. Kp = 64*ceil(3F/64). */
+int onssen_pack_phase_input_f16(const float* x_mag, const float* mask, long long mask_stride,
+                                const float* x_phase, int B, int T, int F, void* out, int Kp, void* stream);
+
+/* out = F.normalize(x + residual, dim=-1) over (re,im) pairs (phase_network.py:63-66). */
+int onssen_add_l2norm_pairs(const float* x, const float* residual, long long npairs, float* out, void* stream);
+
+/* loss_mask_psa (onssen/loss/loss_mask.py:25-40): per utterance sum |mask*noisy - min(noisy, relu(clean*cos))| */
+int onssen_loss_l1_psa_fwd(const float* mask, const float* mag_noisy, const float* mag_clean,
+                           const float* cos_diff, int B, int N, float* out, void* stream);
+
+/* loss_mask_msa (onssen/loss/loss_mask.py:6-22): nn.MSELoss()(a, b) -> out[0]. scratch: 256 doubles. */
+int onssen_loss_mse_fwd(const float* a, const float* b, long long n, float* out, void* scratch, void* stream);
+
+/* phase term of loss_phase (onssen/loss/loss_phase.py:26-35): per utterance
+ * -sum mag_mix * (cos_sim(pX, s1) + cos_sim(pY, s2)), (X,Y) = (A,B) when perm[b]==0 else (B,A);
+ * phases [B][N][2], cosine_similarity eps 1e-8. */
+int onssen_loss_phase_cos_fwd(const float* phase_a, const float* phase_b, const float* phase_s1,
+                              const float* phase_s2, const float* mag_mix, const int32_t* perm, int B, int N,
+                              float* out, void* stream);
 
 #ifdef __cplusplus
 }

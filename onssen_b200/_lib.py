@@ -23,7 +23,7 @@ _SIGNATURES = {
     "onssen_version": (ctypes.c_char_p, []),
     "onssen_error_string": (ctypes.c_char_p, [c_int]),
     "onssen_num_sms": (c_int, []),
-    "onssen_stft_features": (c_int, [c_vp] * 3 + [c_int] * 4 + [c_vp, c_int] + [c_vp] * 10 + [c_vp]),
+    "onssen_stft_features": (c_int, [c_vp] * 3 + [c_int] * 4 + [c_vp, c_int] + [c_vp] * 10 + [c_vp, c_vp]),
     "onssen_one_hot_vad": (c_int, [c_vp] * 4 + [c_f, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_istft_scratch_bytes": (c_sz, [c_int] * 4),
     "onssen_istft_masked": (c_int, [c_vp] * 3 + [c_int] * 6 + [c_vp, c_vp, c_vp]),
@@ -33,6 +33,7 @@ _SIGNATURES = {
     "onssen_gemm_l2norm_supported": (c_int, [c_int]),
     "onssen_gemm_f16": (c_int, [c_vp] * 4 + [c_int] * 3 + [c_ll] * 3 + [c_int] * 4 + [c_vp]),
     "onssen_blstm_rec_workspace_bytes": (c_sz, [c_int, c_int]),
+    "onssen_blstm_rec_set_trace": (None, [c_vp]),
     "onssen_blstm_rec_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_f, c_ull, c_ull, c_vp, c_sz,
                                      c_int, c_vp]),
     "onssen_bn_num_chunks": (c_int, [c_int]),
@@ -44,6 +45,12 @@ _SIGNATURES = {
     "onssen_loss_dc_fwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                                    c_vp]),
     "onssen_loss_pit_l1_fwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 5 + [c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_mul_pack_f16": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_int, c_vp]),
+    "onssen_pack_phase_input_f16": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "onssen_add_l2norm_pairs": (c_int, [c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "onssen_loss_l1_psa_fwd": (c_int, [c_vp] * 4 + [c_int, c_int, c_vp, c_vp]),
+    "onssen_loss_mse_fwd": (c_int, [c_vp, c_vp, c_ll, c_vp, c_vp, c_vp]),
+    "onssen_loss_phase_cos_fwd": (c_int, [c_vp] * 6 + [c_int, c_int, c_vp, c_vp]),
 }
 
 _lib = None
@@ -55,7 +62,9 @@ REC_EVENTS = None
 _KERNELS_PER_CALL = {"onssen_stft_features": 2, "onssen_one_hot_vad": 1, "onssen_istft_masked": 2,
                      "onssen_pack_input_f16": 1, "onssen_lstm_pack_layer": 3, "onssen_pack_linear_f16": 1,
                      "onssen_gemm_f16": 1, "onssen_blstm_rec_fwd": 1, "onssen_bn_forward_f16": 3,
-                     "onssen_cast_f16": 1, "onssen_loss_dc_fwd": 3, "onssen_loss_pit_l1_fwd": 1}
+                     "onssen_cast_f16": 1, "onssen_loss_dc_fwd": 4, "onssen_loss_pit_l1_fwd": 1,
+                     "onssen_mul_pack_f16": 1, "onssen_pack_phase_input_f16": 1, "onssen_add_l2norm_pairs": 1,
+                     "onssen_loss_l1_psa_fwd": 1, "onssen_loss_mse_fwd": 2, "onssen_loss_phase_cos_fwd": 1}
 
 
 class OnssenB200Error(RuntimeError):
@@ -124,7 +133,7 @@ def hp_of(H):
 
 
 # ------------------------------------------------------------------------------------------------ featurizer
-def stft_features(wav_mix, wav_s1, wav_s2, n_fft, hop, crop_start, T, want):
+def stft_features(wav_mix, wav_s1, wav_s2, n_fft, hop, crop_start, T, want, lengths=None):
     """want: iterable of output names among feature, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2, ph_mix, ph_s1,
     ph_s2, feat_max. Returns dict name -> tensor."""
     lib = load()
@@ -147,7 +156,9 @@ def stft_features(wav_mix, wav_s1, wav_s2, n_fft, hop, crop_start, T, want):
     rc = lib.onssen_stft_features(_p(wav_mix), _p(wav_s1), _p(wav_s2), B, ns, n_fft, hop, _p(crop_start), T,
                                   _p(g("feature")), _p(g("mag_mix")), _p(g("mag_s1")), _p(g("mag_s2")),
                                   _p(g("cos_s1")), _p(g("cos_s2")), _p(g("ph_mix")), _p(g("ph_s1")), _p(g("ph_s2")),
-                                  _p(g("feat_max")), _stream())
+                                  _p(g("feat_max")),
+                                  _p(None if lengths is None else _req(lengths.to(device=dev, dtype=torch.int32),
+                                                                       torch.int32, "lengths")), _stream())
     _check(rc, "onssen_stft_features")
     return out
 
@@ -287,7 +298,7 @@ def loss_dc_fwd(emb, label, mag):
     l = torch.empty(B, device=dev, dtype=torch.float32)
     msum = torch.empty(B, device=dev, dtype=torch.float32)
     nchunk = lib.onssen_loss_dc_num_chunks(N)
-    scratch = torch.empty(B * nchunk * (D * D + D * S + S * S + 4), device=dev, dtype=torch.float32)
+    scratch = torch.empty(B * (nchunk + 1) * (D * D + D * S + S * S + 4), device=dev, dtype=torch.float32)
     rc = lib.onssen_loss_dc_fwd(_p(_req(emb, torch.float32, "embedding")), _p(_req(label, None, "label")),
                                 _DT[label.dtype], _p(_req(mag, torch.float32, "mag_mix")), B, N, D, S, _p(loss_bb),
                                 _p(l), _p(msum), _p(scratch), _stream())
@@ -308,3 +319,65 @@ def loss_pit_l1_fwd(mask_a, mask_b, mask_stride, mag_mix, mag_s1, mag_s2, cos_s1
                                     _p(perm), _stream())
     _check(rc, "onssen_loss_pit_l1_fwd")
     return out, perm
+
+
+# ------------------------------------------------------------------------------------------------ enhance / phase-net
+def mul_pack_f16(a, b):
+    lib = load()
+    M, F = a.shape
+    Kp = (F + 63) // 64 * 64
+    out = torch.empty(M, Kp, device=a.device, dtype=torch.float16)
+    _check(lib.onssen_mul_pack_f16(_p(_req(a, torch.float32)), _p(_req(b, torch.float32)), M, F, _p(out), Kp,
+                                   _stream()), "onssen_mul_pack_f16")
+    return out
+
+
+def pack_phase_input_f16(x_mag, mask, mask_stride, x_phase):
+    lib = load()
+    B, T, F = x_mag.shape
+    Kp = (3 * F + 63) // 64 * 64
+    out = torch.empty(T * B, Kp, device=x_mag.device, dtype=torch.float16)
+    rc = lib.onssen_pack_phase_input_f16(_p(_req(x_mag, torch.float32)), _p(mask), mask_stride,
+                                         _p(_req(x_phase, torch.float32)), B, T, F, _p(out), Kp, _stream())
+    _check(rc, "onssen_pack_phase_input_f16")
+    return out
+
+
+def add_l2norm_pairs(x, residual):
+    lib = load()
+    out = torch.empty_like(x)
+    _check(lib.onssen_add_l2norm_pairs(_p(_req(x, torch.float32)), _p(_req(residual, torch.float32)), x.numel() // 2,
+                                       _p(out), _stream()), "onssen_add_l2norm_pairs")
+    return out
+
+
+def loss_l1_psa_fwd(mask, noisy, clean, cosd):
+    lib = load()
+    B = noisy.shape[0]
+    N = noisy.numel() // B
+    out = torch.empty(B, device=noisy.device, dtype=torch.float32)
+    rc = lib.onssen_loss_l1_psa_fwd(_p(_req(mask, torch.float32)), _p(_req(noisy, torch.float32)),
+                                    _p(_req(clean, torch.float32)), _p(_req(cosd, torch.float32)), B, N, _p(out),
+                                    _stream())
+    _check(rc, "onssen_loss_l1_psa_fwd")
+    return out
+
+
+def loss_mse_fwd(a, b):
+    lib = load()
+    out = torch.empty(1, device=a.device, dtype=torch.float32)
+    scratch = torch.empty(256, device=a.device, dtype=torch.float64)
+    _check(lib.onssen_loss_mse_fwd(_p(_req(a, torch.float32)), _p(_req(b, torch.float32)), a.numel(), _p(out),
+                                   _p(scratch), _stream()), "onssen_loss_mse_fwd")
+    return out[0]
+
+
+def loss_phase_cos_fwd(pa, pb, s1, s2, mag, perm):
+    lib = load()
+    B = mag.shape[0]
+    N = mag.numel() // B
+    out = torch.empty(B, device=mag.device, dtype=torch.float32)
+    rc = lib.onssen_loss_phase_cos_fwd(*[_p(_req(t, torch.float32)) for t in (pa, pb, s1, s2, mag)],
+                                       _p(_req(perm, torch.int32)), B, N, _p(out), _stream())
+    _check(rc, "onssen_loss_phase_cos_fwd")
+    return out

@@ -44,7 +44,7 @@ struct GemmParams {
 };
 
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
-                              4 * EPI_WARP_FLOATS * 4 + 256;
+                              4 * EPI_WARP_FLOATS * 4 + 4 * MAX_BN * 4 /*per-warp bias tile*/ + 256;
 
 __device__ __forceinline__ float act_apply(float x, int epi) {
   if (epi == 1) return 1.0f / (1.0f + __expf(-x));
@@ -71,7 +71,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 4 * EPI_WARP_FLOATS);
+  float* bias_stage = epi_stage + 4 * EPI_WARP_FLOATS;   // [4 warps][MAX_BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_stage + 4 * MAX_BN);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -160,6 +161,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue (4 warps) =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     float* stg = epi_stage + (warp - 2) * EPI_WARP_FLOATS;
+    float* bias_s = bias_stage + (warp - 2) * MAX_BN;
     const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.N & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int it = 0;
@@ -170,6 +172,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int n_blk = tile / p.num_m_blocks;
       const int m0 = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
+      // this tile's bias slice -> warp-private smem (overlaps the wait for the accumulator)
+      for (int i = lane; i < BN; i += 32)
+        bias_s[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      __syncwarp();
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * MAX_BN;
@@ -199,7 +205,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float f[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-              f[j] = __uint_as_float(v[j]) + __ldg(p.bias + nb + j);
+              f[j] = __uint_as_float(v[j]) + bias_s[g * D + j];
               ss = fmaf(f[j], f[j], ss);
             }
             const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
@@ -236,18 +242,21 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 16; j < 32; ++j) v[j] = 0;
           }
           tmem_wait_ld();
+          auto stage_chunk = [&](auto act) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o4;
-            float* o = reinterpret_cast<float*>(&o4);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int n = nb + j + jj;
-              const float b = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
-              o[jj] = act_apply(__uint_as_float(v[j + jj]) + b, p.epi);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);   // smem broadcast
+              float4 o4;
+              o4.x = act(__uint_as_float(v[j]) + b4.x);
+              o4.y = act(__uint_as_float(v[j + 1]) + b4.y);
+              o4.z = act(__uint_as_float(v[j + 2]) + b4.z);
+              o4.w = act(__uint_as_float(v[j + 3]) + b4.w);
+              *reinterpret_cast<float4*>(stg + lane * PITCH + j) = o4;
             }
-            *reinterpret_cast<float4*>(stg + lane * PITCH + j) = o4;
-          }
+          };
+          if (p.epi == 1) stage_chunk([](float x) { return 1.0f / (1.0f + __expf(-x)); });
+          else if (p.epi == 2) stage_chunk([](float x) { return fmaxf(x, 0.0f); });
+          else stage_chunk([](float x) { return x; });
           __syncwarp();
           const int ncols = min(32, min(BN - c0, p.N - nb));
           if (vec_ok) {

@@ -84,10 +84,20 @@ loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ lab
     __syncthreads();
     for (int pnt = g; pnt < np; pnt += NG) {
       float rv[TS], cv[TS];
+      if constexpr ((TS & 1) == 0) {   // D*4 and TS*4 bytes are multiples of 8: 64-bit smem loads
 #pragma unroll
-      for (int i = 0; i < TS; ++i) {
-        rv[i] = ma_s[pnt * D + ti * TS + i];
-        cv[i] = a_s[pnt * D + tj * TS + i];
+        for (int i = 0; i < TS; i += 2) {
+          const float2 r2 = *reinterpret_cast<const float2*>(ma_s + pnt * D + ti * TS + i);
+          const float2 c2 = *reinterpret_cast<const float2*>(a_s + pnt * D + tj * TS + i);
+          rv[i] = r2.x; rv[i + 1] = r2.y;
+          cv[i] = c2.x; cv[i + 1] = c2.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+          rv[i] = ma_s[pnt * D + ti * TS + i];
+          cv[i] = a_s[pnt * D + tj * TS + i];
+        }
       }
 #pragma unroll
       for (int i = 0; i < TS; ++i)
@@ -204,7 +214,19 @@ loss_dc_partial_generic(const float* __restrict__ emb, const LT* __restrict__ la
   }
 }
 
-// per-utterance: ordered sum over chunks, norms, l_b and sum(m)_b
+// ordered (deterministic) sum of the per-chunk partial records: grid (ceil(R/256), B) -> summed[b][R]
+__global__ void __launch_bounds__(256) loss_dc_reduce_kernel(const float* __restrict__ scratch, int nchunk, int R,
+                                                             float* __restrict__ summed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= R) return;
+  const float* base = scratch + (long long)b * nchunk * R + i;
+  float v = 0.f;
+  for (int c = 0; c < nchunk; ++c) v += base[(long long)c * R];
+  summed[(long long)b * R + i] = v;
+}
+
+// per-utterance: norms, l_b and sum(m)_b from the summed record (nchunk == 1 layout)
 __global__ void __launch_bounds__(256) loss_dc_final_kernel(const float* __restrict__ scratch, int nchunk, int D,
                                                             int S, int fast_layout, float* __restrict__ l_out,
                                                             float* __restrict__ msum_out) {
@@ -280,8 +302,9 @@ int dispatch_dc(const float* emb, const void* label, const float* mag, int B, in
   *fast = 1;
   if (S == 2 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0) {
     switch (D) {
-      case 20: return launch_dc_fast<20, 5, LT>(emb, label, mag, B, N, scratch, s);
-      case 40: return launch_dc_fast<40, 5, LT>(emb, label, mag, B, N, scratch, s);
+      // 10x10 register tiles: 100 FMA per 10 64-bit smem loads -> FMA-bound instead of smem-bound
+      case 20: return launch_dc_fast<20, 10, LT>(emb, label, mag, B, N, scratch, s);
+      case 40: return launch_dc_fast<40, 10, LT>(emb, label, mag, B, N, scratch, s);
       case 8: return launch_dc_fast<8, 4, LT>(emb, label, mag, B, N, scratch, s);
       case 16: return launch_dc_fast<16, 4, LT>(emb, label, mag, B, N, scratch, s);
       case 32: return launch_dc_fast<32, 4, LT>(emb, label, mag, B, N, scratch, s);
@@ -359,7 +382,11 @@ extern "C" int onssen_loss_dc_fwd(const float* emb, const void* label, int label
     default: return ONSSEN_ERR_ARG;
   }
   if (rc != ONSSEN_OK) return rc;
-  loss_dc_final_kernel<<<B, 256, 0, s>>>(scratch, onssen_loss_dc_num_chunks(N), D, S, fast, l, mag_sum);
+  const int nchunk = onssen_loss_dc_num_chunks(N);
+  const int R = fast ? (D * D + D * 2 + 4) : (D * D + D * S + S * S + 1);
+  float* summed = scratch + (long long)B * nchunk * (D * D + D * S + S * S + 4);   // behind the partial records
+  loss_dc_reduce_kernel<<<dim3((R + 255) / 256, B), 256, 0, s>>>(scratch, nchunk, R, summed);
+  loss_dc_final_kernel<<<B, 256, 0, s>>>(summed, 1, D, S, fast, l, mag_sum);
   if (loss_bb) loss_dc_outer_kernel<<<(B * B + 255) / 256, 256, 0, s>>>(l, mag_sum, B, loss_bb);
   return ONSSEN_CHECK_LAUNCH();
 }

@@ -8,18 +8,20 @@
 //
 // Decomposition: grid = 2 directions x S batch slices x nrb row blocks, all CTAs
 // co-resident (cooperative launch, 1 CTA / SM).  CTA (dir, slice, rb) owns 32 hidden units = 128 gate rows
-// (row r = 4*unit + gate) and keeps its 128 x Hp fp16 slice of W_hh resident in shared memory for the whole
-// sequence (weights are read from HBM exactly once per layer).  Per step:
-//   control thread : wait until all nrb CTAs of its (dir,slice) group published h_{t-1}  (global counter,
-//                    acquire) -> cp.async.bulk h_{t-1} [NBP x Hp fp16, pre-laid-out as UMMA B operand]
-//                    -> Hp/16 x tcgen05.mma (M=128 gate rows, N=NBP batch columns, K=16) -> commit
-//   4 gate warps   : tcgen05.ld their 32 TMEM lanes (one gate row per thread, NB batch columns),
-//                    add the prefetched input pre-activation, sigmoid/tanh (one transcendental chain per
-//                    thread: the 4 gates of a unit sit in 4 adjacent lanes), exchange the activated gates
-//                    through a warp-private smem tile, update c (registers) and h, publish h_t (fp16) to the
-//                    group's exchange buffer and to the layer output, then release-increment the counter.
-// The recurrent contraction runs on tensor cores (fp16 operands, fp32 accumulate); everything else is
-// latency-bound control: the design minimises the serial chain per step, not bytes.
+// (row r = 4*unit + gate).  Its 128 x Hp fp16 slice of W_hh is loaded ONCE into TENSOR MEMORY (lane = gate
+// row, two fp16 per 32-bit column: 304 of the 512 TMEM columns at H=600) and stays there for the whole
+// sequence as the A operand of tcgen05.mma (TS form): recurrent weights cross HBM once per layer and are
+// never re-streamed through shared memory.  Per step:
+//   control thread : relaxed-poll the group's arrival counter (all nrb CTAs published h_{t-1}), one acquire
+//                    fence -> cp.async.bulk h_{t-1} [NBP x Hp fp16, pre-laid-out as UMMA B operand] into
+//                    smem -> Hp/16 x tcgen05.mma (A: TMEM, B: smem, D: TMEM; M=128, N=NBP, K=16) -> commit
+//   8 gate warps   : tcgen05.ld their TMEM lanes (thread = one gate row, NB/2 batch columns), add the
+//                    prefetched input pre-activation, sigmoid/tanh (tanh(x) = 2*sigmoid(2x)-1 so all gates
+//                    share code), exchange activated gates through a warp-private smem tile (the 4 gates of a
+//                    unit are 4 adjacent lanes), update c (registers) and h, store h_t (fp16) into the group's
+//                    exchange buffer, bar.sync, ONE release-increment of the counter, and only then write the
+//                    layer output (off the critical path).
+// Latency-bound by the per-step serial chain (publish -> poll -> bulk copy -> MMA -> gate math), not by bytes.
 #include "tc05.cuh"
 #include "common.cuh"
 
@@ -28,7 +30,13 @@ namespace {
 
 using namespace tc05;
 
-constexpr int REC_THREADS = 160;  // 4 gate warps + 1 control warp
+constexpr int REC_GATE_WARPS = 8;
+constexpr int REC_THREADS = (REC_GATE_WARPS + 1) * 32;  // 8 gate warps + 1 control warp
+constexpr int TMEM_A_COL = 128;                         // first TMEM column of the resident W_hh slice
+constexpr int NACC = 4;   // independent accumulators (columns a*NBP): back-to-back MMAs into ONE accumulator
+                          // serialise on the ~70-cycle accumulate latency when N is this small
+constexpr int TRACE_S0 = 100;
+long long* g_trace_ptr = nullptr;
 
 struct RecParams {
   const float* gates;
@@ -39,42 +47,79 @@ struct RecParams {
   unsigned int* flags;
   int B, T, H, Hp, nrb, S, Bs;
   float dropout_p;
-  unsigned long long seed, offset;
+  unsigned int seed_lo, seed_hi;
+  long long* trace;  // debug: clock64 stamps of CTA 0, steps [TRACE_S0, TRACE_S0+4)
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
-  // splitmix64 finaliser -> 24-bit uniform in [0,1)
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(unsigned int)(z >> 40) * (1.0f / 16777216.0f);
+// 32-bit counter hash -> uniform [0,1): inter-layer dropout mask (statistical parity only, like cuDNN's)
+__device__ __forceinline__ float hash_uniform32(unsigned int seed_lo, unsigned int seed_hi, unsigned int idx) {
+  unsigned int x = idx ^ seed_lo;
+  x *= 0x9E3779B1u; x ^= x >> 15;
+  x *= 0x85EBCA77u; x ^= x >> 13;
+  x += seed_hi;
+  x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+#define REC_TRACE(slot)                                                             \
+  do {                                                                              \
+    if (p.trace != nullptr && blockIdx.x == 0 && s >= TRACE_S0 && s < TRACE_S0 + 4) \
+      p.trace[(s - TRACE_S0) * 16 + (slot)] = clock64();                            \
+  } while (0)
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* v) {
+  if constexpr (N == 4) tmem_ld4(taddr, v);
+  if constexpr (N == 8) tmem_ld8(taddr, v);
+  if constexpr (N == 12) { tmem_ld8(taddr, v); tmem_ld4(taddr + 8, v + 8); }
+  if constexpr (N == 16) tmem_ld16(taddr, v);
+}
+
+// Self-validating exchange: |h_t| <= 1, so bit 14 (top exponent bit) of every fp16 h is always 0 and is used
+// as a per-element step-parity flag.  A buffer (selected by s&1) is rewritten every 2 steps with the flag bit
+// toggled, so a reader knows an element is fresh from the element itself: no fences, no counters, no extra
+// bytes (the NCCL "LL" idea at 1 bit per element).  Stores are 4-byte relaxed (two units of one column).
+__device__ __forceinline__ void st_relaxed_u32(void* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
 }
 
 template <int NB, bool TC>
 __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecParams p) {
   constexpr int NBP = NB <= 16 ? 16 : 32;  // MMA N / rows of the h operand tile
+  constexpr int NBH = NB / 2;              // batch columns per gate-warp half
   constexpr int XP = NB + 1;               // exchange tile pitch (floats)
+  constexpr int GT = REC_GATE_WARPS * 32;  // gate threads
   extern __shared__ __align__(128) uint8_t smem[];
   const int Hp = p.Hp;
-  const uint32_t w_bytes = (uint32_t)Hp * 128u * 2u;
+  const uint32_t w_bytes = TC ? 0u : (uint32_t)Hp * 128u * 2u;   // SIMT validation path keeps W in smem
   const uint32_t h_bytes = (uint32_t)Hp * NBP * 2u;
   uint8_t* w_s = smem;
   uint8_t* h_s = smem + w_bytes;
   float* xch = reinterpret_cast<float*>(h_s + h_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 128 * XP + ((128 * XP) & 1));
   uint64_t* wbar = bars;
-  uint64_t* hbar = bars + 1;
-  uint64_t* mbar = bars + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* mbar = bars + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -85,124 +130,187 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
   const int b0 = sl * p.Bs;
   const int nb_valid = min(p.Bs, p.B - b0);
   const int T = p.T;
-  unsigned int* flag = p.flags + dir * p.S + sl;
-  const size_t hbuf_group = (size_t)Hp * NBP;  // halves per (parity,dir,slice)
-  __half* hbuf0 = p.hbuf + ((size_t)(0 * 2 + dir) * p.S + sl) * hbuf_group;
-  __half* hbuf1 = p.hbuf + ((size_t)(1 * 2 + dir) * p.S + sl) * hbuf_group;
+  // exchange buffers: per (parity, dir, slice) one operand tile [k/8][n][k%8] fp16 with flag bits
+  const size_t ll_group_bytes = (size_t)Hp * NBP * 2;
+  uint8_t* ll0 = reinterpret_cast<uint8_t*>(p.hbuf) + ((size_t)(0 * 2 + dir) * p.S + sl) * ll_group_bytes;
+  uint8_t* ll1 = reinterpret_cast<uint8_t*>(p.hbuf) + ((size_t)(1 * 2 + dir) * p.S + sl) * ll_group_bytes;
+  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.whh) + ((size_t)dir * p.nrb + rb) * ((size_t)Hp * 256);
 
-  if (warp == 4) {
+  if (warp == REC_GATE_WARPS) {
     if (lane == 0) {
       mbar_init(wbar, 1);
-      mbar_init(hbar, 1);
       mbar_init(mbar, 1);
       fence_mbar_init();
     }
     __syncwarp();
-    if (TC) tmem_alloc(tmem_ptr, 32);
+    if (TC) tmem_alloc(tmem_ptr, 512);
   }
+  // zero the h operand tile once (rows n >= NB are never written afterwards and must read as zero)
+  for (uint32_t i = tid; i < h_bytes / 16; i += REC_THREADS) reinterpret_cast<uint4*>(h_s)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   uint32_t tmem_base = 0;
   if (TC) tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
-    // ===================== control warp =====================
-    if (lane == 0) {
-      // resident recurrent weights: one contiguous slab per (dir, rb)
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.whh) + ((size_t)dir * p.nrb + rb) * w_bytes;
-      mbar_arrive_expect_tx(wbar, w_bytes);
-      constexpr uint32_t CH = 32768;
-      for (uint32_t off = 0; off < w_bytes; off += CH) {
-        const uint32_t n = (w_bytes - off) < CH ? (w_bytes - off) : CH;
-        bulk_load(w_s + off, wsrc + off, n, wbar);
+  // ---- resident weights: TMEM (product path) or smem (SIMT validation path) ----
+  if (TC) {
+    if (warp < 4) {
+      // thread = gate row r = 32*warp + lane: its Hp fp16 = Hp/2 words go to lane r, columns TMEM_A_COL..
+      const uint4* src = reinterpret_cast<const uint4*>(wsrc + (size_t)(warp * 32 + lane) * Hp * 2);
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + TMEM_A_COL;
+      const int words = Hp / 2;
+      int c = 0;
+      for (; c + 32 <= words; c += 32) {
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 q4 = __ldg(src + c / 4 + i);
+          v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
+        }
+        tmem_st32(trow + c, v);
       }
-      if (TC) mbar_wait(wbar, 0);
+      if (c < words) {   // Hp multiple of 32 -> remainder is exactly 16 words
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 q4 = __ldg(src + c / 4 + i);
+          v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
+        }
+        tmem_st16(trow + c, v);
+      }
+      tmem_wait_st();
     }
-    __syncwarp();
-    const uint32_t idesc = make_idesc_f16(128, NBP);
-    const uint32_t w_addr = smem_u32(w_s);
-    const uint32_t h_addr = smem_u32(h_s);
-    for (int s = 1; s < T; ++s) {
-      if (lane == 0) {
-        const unsigned int target = (unsigned int)p.nrb * (unsigned int)s;
-        while (ld_acquire_u32(flag) < target) {
-        }
-        fence_proxy_async();
-        const __half* hsrc = ((s - 1) & 1) ? hbuf1 : hbuf0;
-        mbar_arrive_expect_tx(hbar, h_bytes);
-        bulk_load(h_s, hsrc, h_bytes, hbar);
-        if (TC) {
-          mbar_wait(hbar, (s - 1) & 1);
-          tc_fence_after_sync();
-          const int ksteps = Hp / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t da = make_smem_desc(w_addr + ks * 4096, 2048, 128, 0);
-            const uint64_t db = make_smem_desc(h_addr + ks * (2 * NBP * 16), NBP * 16, 128, 0);
-            umma_f16(tmem_base, da, db, idesc, ks != 0);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+  } else if (warp == REC_GATE_WARPS && lane == 0) {
+    mbar_arrive_expect_tx(wbar, w_bytes);
+    constexpr uint32_t CH = 32768;
+    for (uint32_t off = 0; off < w_bytes; off += CH) {
+      const uint32_t n = (w_bytes - off) < CH ? (w_bytes - off) : CH;
+      bulk_load(w_s + off, wsrc + off, n, wbar);
+    }
+  }
+
+  if (warp == REC_GATE_WARPS) {
+    // ===================== MMA warp =====================
+    // The whole warp runs the loop converged so descriptors / TMEM addresses live in uniform registers;
+    // only the tcgen05 instructions are predicated on the elected lane (a single divergent lane pays ~200
+    // cycles of R2UR traffic per MMA, see scripts/microbench/mma_cost.cu).
+    if (TC) {
+      const bool leader = elect_one();
+      const uint32_t idesc = make_idesc_f16(128, NBP);
+      const uint32_t h_addr = smem_u32(h_s);
+      const int ksteps = Hp / 16;
+      constexpr uint64_t DB_STEP = (2 * NBP * 16) >> 4;   // start-address field counts 16-byte units
+      for (int s = 1; s < T; ++s) {
+        // all gate threads have written + fenced their part of h_{s-1} and drained the accumulators
+        named_bar_sync(3, REC_THREADS);
+        tc_fence_after_sync();
+        if (lane == 0) REC_TRACE(3);
+        // blocks of 8 k-steps whose operands are computed independently from the block base: incremental
+        // updates would chain every MMA behind ~10-cycle uniform-datapath adds
+        uint64_t db0 = make_smem_desc(h_addr, NBP * 16, 128, 0);
+        uint32_t ta0 = tmem_base + TMEM_A_COL;
+        for (int ks0 = 0; ks0 < ksteps; ks0 += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (ks0 + j < ksteps && leader)
+              umma_f16_ts(tmem_base + (j % NACC) * NBP, ta0 + 8 * j, db0 + (uint64_t)j * DB_STEP, idesc,
+                          (ks0 + j) >= NACC);
           }
-          umma_commit(mbar);
+          ta0 += 64;           // 8 k-steps x (K=16 fp16 = 8 TMEM columns)
+          db0 += 8 * DB_STEP;
         }
+        if (leader) umma_commit(mbar);
+        __syncwarp();
+        if (lane == 0) REC_TRACE(4);
       }
-      __syncwarp();
-      // wait until the gate warps have drained TMEM / finished reading h_s for this step
-      named_bar_sync(2, REC_THREADS);
-      tc_fence_after_sync();
     }
   } else {
     // ===================== gate warps =====================
-    const int r = tid;            // gate row inside the row block: r = 4*ul + gate
+    const int q = warp & 3;         // TMEM lane quarter
+    const int half = warp >> 2;     // which half of the batch columns this warp owns
+    const int r = q * 32 + lane;    // gate row inside the row block: r = 4*ul + gate
     const int gate = r & 3;
-    const int ul = r >> 2;        // unit inside the row block (0..31)
-    const int u = rb * 32 + ul;   // padded hidden unit index
+    const int ul = r >> 2;          // unit inside the row block (0..31)
+    const int u = rb * 32 + ul;     // padded hidden unit index
+    const int jbase = half * NBH;
     const float ak = (gate == 2) ? 2.0f : 1.0f;   // act(x) = ak*sigmoid(ak*x) + ab  (tanh for gate g)
     const float ab = (gate == 2) ? -1.0f : 0.0f;
     const long long ldg = 2LL * 4 * Hp;
-    const long long ldy = 2LL * Hp;
+    const int ldy = 2 * Hp;
     const float* gcol = p.gates + (long long)dir * 4 * Hp + rb * 128 + r;
     const float keep_scale = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+    // gather: 16-byte chunks (kc, n) = 8 consecutive units of one column; chunk c = kc*NBP + n at byte 16*c
+    // in both the global exchange tile and the smem operand tile.  Thread handles c = tid + GT*i.
+    const int nchunks = Hp * NBP / 8;
+    constexpr int MAXCH = NBP == 16 ? 6 : 12;
+    const int my_chunks = (nchunks - tid + GT - 1) / GT;   // <= MAXCH (checked on the host)
+    unsigned int want_mask = 0;                            // chunks of real batch columns only (pads stay 0)
+    for (int i = 0; i < my_chunks; ++i)
+      if (((tid + GT * i) % NBP) < nb_valid) want_mask |= 1u << i;
 
-    float c_state[NB / 4];
+    float c_state[NBH / 4];
 #pragma unroll
-    for (int i = 0; i < NB / 4; ++i) c_state[i] = 0.f;
-    float gpre[NB];
+    for (int i = 0; i < NBH / 4; ++i) c_state[i] = 0.f;
+    // input pre-activations are prefetched TWO steps ahead (HBM latency under load exceeds the MMA phase)
+    // All prefetch loads are UNCONDITIONAL (a `cond ? load : 0` select would make the warp wait for the load
+    // at the select): pad columns / out-of-range steps read a valid neighbouring address and the value is
+    // simply never used for anything that is kept (pad columns of h are neither gathered nor written out).
+    float gpre[NBH], gnext[NBH];
+    int jcl[NBH];   // clamped batch column per register slot
+#pragma unroll
+    for (int j = 0; j < NBH; ++j) jcl[j] = b0 + min(jbase + j, nb_valid - 1);
     {
       const int t0 = dir ? T - 1 : 0;
+      const int t1 = T > 1 ? (dir ? T - 2 : 1) : t0;
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        gpre[j] = (j < nb_valid) ? __ldcs(gcol + ((long long)t0 * p.B + b0 + j) * ldg) : 0.f;
+      for (int j = 0; j < NBH; ++j) {
+        gpre[j] = __ldcs(gcol + ((long long)t0 * p.B + jcl[j]) * ldg);
+        gnext[j] = __ldcs(gcol + ((long long)t1 * p.B + jcl[j]) * ldg);
+      }
     }
     if (!TC) mbar_wait(wbar, 0);
 
     for (int s = 0; s < T; ++s) {
       const int t = dir ? T - 1 - s : s;
-      float acc[NB];
+      float acc[NBH];
       if (s == 0) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+        for (int j = 0; j < NBH; ++j) acc[j] = 0.f;
       } else if (TC) {
         mbar_wait(mbar, (s - 1) & 1);
         tc_fence_after_sync();
-        uint32_t v[NBP];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-        if (NBP == 16) tmem_ld16(taddr, v); else tmem_ld32(taddr, v);
+        if (tid == 0) REC_TRACE(8);
+        uint32_t v[NACC][NBH];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+          tmem_ld_n<NBH>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * NBP + jbase, v[a]);
         tmem_wait_ld();
+        const int nacc = min(NACC, Hp / 16);   // accumulators actually written (tiny Hp: fewer k-steps)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j] = __uint_as_float(v[j]);
-        tc_fence_before_sync();
-        asm volatile("bar.arrive 2, %0;" ::"r"(REC_THREADS) : "memory");
+        for (int j = 0; j < NBH; ++j) {
+          const float a0 = __uint_as_float(v[0][j]);
+          const float a1 = nacc > 1 ? __uint_as_float(v[1][j]) : 0.f;
+          const float a2 = nacc > 2 ? __uint_as_float(v[2][j]) : 0.f;
+          const float a3 = nacc > 3 ? __uint_as_float(v[3][j]) : 0.f;
+          acc[j] = (a0 + a1) + (a2 + a3);
+        }
+        if (tid == 0) REC_TRACE(9);
       } else {
-        mbar_wait(hbar, (s - 1) & 1);
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-        const uint4* wv = reinterpret_cast<const uint4*>(w_s);
+        for (int j = 0; j < NBH; ++j) acc[j] = 0.f;
+        const uint4* wv = reinterpret_cast<const uint4*>(w_s + (size_t)r * Hp * 2);
         const uint4* hv = reinterpret_cast<const uint4*>(h_s);
         for (int kc = 0; kc < Hp / 8; ++kc) {
-          const uint4 w8 = wv[kc * 128 + r];
+          const uint4 w8 = wv[kc];
           const __half2* wh = reinterpret_cast<const __half2*>(&w8);
 #pragma unroll
-          for (int j = 0; j < NB; ++j) {
-            const uint4 h8 = hv[kc * NBP + j];
+          for (int j = 0; j < NBH; ++j) {
+            const uint4 h8 = hv[kc * NBP + jbase + j];
             const __half2* hh = reinterpret_cast<const __half2*>(&h8);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -213,28 +321,25 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
             }
           }
         }
-        asm volatile("bar.arrive 2, %0;" ::"r"(REC_THREADS) : "memory");
+        named_bar_sync(1, GT);   // everyone finished reading h_s before it is overwritten below
       }
 
-      // activation of this thread's gate for all NB batch columns
+      // activation of this thread's gate for its NBH batch columns
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
+      for (int j = 0; j < NBH; ++j) {
         const float pre = acc[j] + gpre[j];
-        xch[r * XP + j] = fmaf(ak, sigmoid_f(ak * pre), ab);
-      }
-      // prefetch next step's input pre-activations (hidden behind this step's tail + next step's wait)
-      if (s + 1 < T) {
-        const int tn = dir ? t - 1 : t + 1;
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-          gpre[j] = (j < nb_valid) ? __ldcs(gcol + ((long long)tn * p.B + b0 + j) * ldg) : 0.f;
+        xch[r * XP + jbase + j] = fmaf(ak, sigmoid_f(ak * pre), ab);
       }
       __syncwarp();
+      if (tid == 0) REC_TRACE(10);
 
-      __half* hdst = (s & 1) ? hbuf1 : hbuf0;
+      uint8_t* lldst = (s & 1) ? ll1 : ll0;
+      const unsigned int fbit = (((unsigned int)s >> 1) & 1u) ^ 1u;   // buffers start zeroed -> first use expects 1
+      const unsigned int fword = fbit ? 0x40004000u : 0u;
+      float hval[NBH / 4];
 #pragma unroll
-      for (int ci = 0; ci < NB / 4; ++ci) {
-        const int j = 4 * ci + gate;  // this lane finishes batch column j of unit ul
+      for (int ci = 0; ci < NBH / 4; ++ci) {
+        const int j = jbase + 4 * ci + gate;  // this lane finishes batch column j of unit ul
         const float* xr = xch + (4 * ul) * XP + j;
         const float gi = xr[0];
         const float gf = xr[XP];
@@ -243,51 +348,100 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
         const float c = fmaf(gf, c_state[ci], gi * gg);
         c_state[ci] = c;
         const float h = go * fmaf(2.0f, sigmoid_f(2.0f * c), -1.0f);
-        // next step's B operand tile: [k/8][n][k%8]
-        hdst[((size_t)(u >> 3) * NBP + j) * 8 + (u & 7)] = __float2half_rn(h);
-        if (j < nb_valid) {
-          const long long m = (long long)t * p.B + b0 + j;
-          float hv = h;
-          if (p.dropout_p > 0.f) {
-            const float rnd = hash_uniform(p.seed, p.offset + (unsigned long long)(m * ldy + dir * Hp + u));
-            hv = rnd < p.dropout_p ? 0.f : h * keep_scale;
-          }
-          if (p.y_h) p.y_h[m * ldy + dir * Hp + u] = __float2half_rn(hv);
-          if (p.y_f) p.y_f[m * ldy + dir * Hp + u] = hv;
+        hval[ci] = h;
+        // publish: units (u, u+1) of column j share one 4-byte word; lane+4 holds unit u+1
+        const float hn = __shfl_down_sync(0xffffffffu, h, 4);
+        if ((ul & 1) == 0) {
+          const __half2 pk = __floats2half2_rn(h, hn);
+          st_relaxed_u32(lldst + ((size_t)((u >> 3) * NBP + j) * 8 + (u & 7)) * 2,
+                         *reinterpret_cast<const unsigned int*>(&pk) | fword);
         }
       }
-      // publish: all 128 gate threads' stores, then one release increment
-      named_bar_sync(1, 128);
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(flag, 1u);
+      if (tid == 0) REC_TRACE(11);
+      // layer output (plain stores, not needed by the other CTAs) and the prefetch two steps ahead are issued
+      // between publish and gather: their latency is absorbed by the wait for the other CTAs' h_t
+#pragma unroll
+      for (int ci = 0; ci < NBH / 4; ++ci) {
+        const int j = jbase + 4 * ci + gate;
+        if (j < nb_valid) {
+          const int m = t * p.B + b0 + j;
+          const long long o = (long long)m * ldy + dir * Hp + u;
+          float hv = hval[ci];
+          if (p.dropout_p > 0.f) {
+            const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)o);
+            hv = rnd < p.dropout_p ? 0.f : hv * keep_scale;
+          }
+          if (p.y_h) p.y_h[o] = __float2half_rn(hv);
+          if (p.y_f) p.y_f[o] = hv;
+        }
+      }
+      {
+        // rotate the prefetch registers and issue the loads for step s+2
+        const int tn = (s + 2 < T) ? (dir ? t - 2 : t + 2) : t;   // clamped: the last two loads are unused
+#pragma unroll
+        for (int j = 0; j < NBH; ++j) {
+          gpre[j] = gnext[j];
+          gnext[j] = __ldcs(gcol + ((long long)tn * p.B + jcl[j]) * ldg);
+        }
+      }
+      if (s + 1 < T) {
+        // gather h_t of the whole group (all nrb producers) into the smem operand tile: spin on the flag bits
+        uint4 v[MAXCH];
+        unsigned int pending = want_mask;
+        while (pending) {
+#pragma unroll
+          for (int i = 0; i < MAXCH; ++i)
+            if (pending & (1u << i)) v[i] = ld_relaxed_v4(lldst + (size_t)(tid + GT * i) * 16);
+#pragma unroll
+          for (int i = 0; i < MAXCH; ++i)
+            if (pending & (1u << i)) {
+              const unsigned int m = 0x40004000u;
+              const bool fresh = ((v[i].x & m) == fword) && ((v[i].y & m) == fword) && ((v[i].z & m) == fword) &&
+                                 ((v[i].w & m) == fword);
+              if (fresh) {
+                *reinterpret_cast<uint4*>(h_s + (size_t)(tid + GT * i) * 16) =
+                    make_uint4(v[i].x & ~m, v[i].y & ~m, v[i].z & ~m, v[i].w & ~m);
+                pending &= ~(1u << i);
+              }
+            }
+        }
+        if (tid == 0) REC_TRACE(12);
+        if (TC) {
+          fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          tc_fence_before_sync();
+          asm volatile("bar.arrive 3, %0;" ::"r"(REC_THREADS) : "memory");
+        } else {
+          named_bar_sync(1, GT);
+        }
+        if (tid == 0) REC_TRACE(13);
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (TC && warp == 4) {
+  if (TC && warp == REC_GATE_WARPS) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 32);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int NB>
+template <int NB, bool TC>
 size_t rec_smem_bytes(int Hp) {
   constexpr int NBP = NB <= 16 ? 16 : 32;
-  return (size_t)Hp * 128 * 2 + (size_t)Hp * NBP * 2 + (size_t)(128 * (NB + 1) + 1) * 4 + 64;
+  return (TC ? 0 : (size_t)Hp * 128 * 2) + (size_t)Hp * NBP * 2 + (size_t)(128 * (NB + 1) + 1) * 4 + 64;
 }
 
 template <int NB, bool TC>
 int launch_rec(RecParams& p, int grid, cudaStream_t stream) {
-  const size_t smem = rec_smem_bytes<NB>(p.Hp);
+  const size_t smem = rec_smem_bytes<NB, TC>(p.Hp);
   auto kern = blstm_rec_kernel<NB, TC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return ONSSEN_ERR_CUDA;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem) != cudaSuccess)
     return ONSSEN_ERR_CUDA;
+  if (per_sm > 1 && TC) per_sm = 1;   // each CTA allocates all 512 TMEM columns
   if (per_sm * num_sms() < grid) return ONSSEN_ERR_RESIDENCY;
   void* args[] = {(void*)&p};
   if (cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream) !=
@@ -299,11 +453,7 @@ int launch_rec(RecParams& p, int grid, cudaStream_t stream) {
 template <bool TC>
 int dispatch_nb(int nb, RecParams& p, int grid, cudaStream_t stream) {
   switch (nb) {
-    case 4: return launch_rec<4, TC>(p, grid, stream);
-    case 8: return launch_rec<8, TC>(p, grid, stream);
-    case 12: return launch_rec<12, TC>(p, grid, stream);
     case 16: return launch_rec<16, TC>(p, grid, stream);
-    case 24: return launch_rec<24, TC>(p, grid, stream);
     case 32: return launch_rec<32, TC>(p, grid, stream);
     default: return ONSSEN_ERR_UNSUPPORTED;
   }
@@ -316,12 +466,15 @@ struct SlicePlan {
 };
 SlicePlan plan_slices(int B, int H) {
   SlicePlan sp{};
-  const int nrb = hp_of(H) / 32;
+  const int Hp = hp_of(H);
+  const int nrb = Hp / 32;
   int smax = num_sms() / (2 * nrb);
-  if (smax < 1) { sp.ok = false; return sp; }
+  // TMEM: NACC accumulators + Hp/2 weight columns; gather: Hp*NBP/8 chunks over 256 gate threads, at most
+  // 6 (NBP=16) / 12 (NBP=32) per thread  <=>  Hp <= 768
+  if (smax < 1 || Hp / 2 + TMEM_A_COL > 512 || Hp > 768) { sp.ok = false; return sp; }
   if (smax > B) smax = B;
   int bs = (B + smax - 1) / smax;
-  static const int opts[] = {4, 8, 12, 16, 24, 32};
+  static const int opts[] = {16, 32};   // NB == NBP: all operand-tile columns are published every step
   int nb = -1;
   for (int o : opts) if (o >= bs) { nb = o; break; }
   if (nb < 0) { sp.ok = false; return sp; }
@@ -337,6 +490,10 @@ SlicePlan plan_slices(int B, int H) {
 }  // namespace onssen
 
 using namespace onssen;
+
+extern "C" void onssen_blstm_rec_set_trace(void* device_buf_64_int64) {
+  g_trace_ptr = (long long*)device_buf_64_int64;
+}
 
 extern "C" size_t onssen_blstm_rec_workspace_bytes(int B, int H) {
   if (B <= 0 || H <= 0) return 0;
@@ -363,7 +520,11 @@ extern "C" int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B
   p.y_h = (__half*)y_h;
   p.y_f = y_f;
   p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H); p.nrb = p.Hp / 32; p.S = sp.S; p.Bs = sp.Bs;
-  p.dropout_p = dropout_p; p.seed = seed; p.offset = offset;
+  p.dropout_p = dropout_p;
+  const unsigned long long mix = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
+  p.seed_lo = (unsigned int)mix;
+  p.seed_hi = (unsigned int)(mix >> 32);
+  p.trace = g_trace_ptr;
   const size_t hbuf_bytes = (size_t)2 * 2 * sp.S * p.Hp * sp.NBP * 2;
   if (workspace_bytes < 256 + hbuf_bytes) return ONSSEN_ERR_ARG;
   p.flags = (unsigned int*)workspace;

@@ -66,19 +66,17 @@ __global__ void pack_wih_kernel(PackArgs a, __half* __restrict__ out) {
 }
 
 __global__ void pack_whh_kernel(PackArgs a, __half* __restrict__ out) {
-  // layout [dir][rb][kc][128][8]
+  // layout [dir][rb][row 0..127][Hp]: one contiguous row-major slab per (dir, row block); a gate thread
+  // streams its own row into its TMEM lane (csrc/lstm_rec.cu)
   const int nrb = a.Hp / 32;
-  const int nkc = a.Hp / 8;
-  const long long total = 2LL * nrb * nkc * 128 * 8;
+  const long long total = 2LL * nrb * 128 * a.Hp;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    long long t = idx;
-    const int e = (int)(t & 7); t >>= 3;
+    const int k = (int)(idx % a.Hp);
+    long long t = idx / a.Hp;
     const int r = (int)(t & 127); t >>= 7;
-    const int kc = (int)(t % nkc); t /= nkc;
     const int rb = (int)(t % nrb);
     const int dir = (int)(t / nrb);
-    const int k = kc * 8 + e;
     int src_row;
     const bool row_ok = decode_row(rb * 128 + r, a.H, src_row);
     float v = 0.f;

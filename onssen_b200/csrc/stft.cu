@@ -19,7 +19,8 @@ namespace {
 struct StftParams {
   const float* wav[3];
   const int32_t* crop_start;
-  int B, ns, N, logN, hop, T, F, frames, nsig;
+  const int32_t* ns_per_utt;   // optional true lengths (<= ns = row pitch); NULL: every row has ns samples
+  int B, ns, N, logN, hop, T, F, nsig;
   float* feature;
   float* mag[3];
   float* cosd[2];
@@ -73,15 +74,17 @@ __global__ void stft_feat_kernel(const StftParams p) {
   const int N = p.N;
   const int tx = threadIdx.x, sig = threadIdx.y, nthr = blockDim.x;
   const int b = blockIdx.y, tt = blockIdx.x;
-  const int fr = (p.crop_start[b] + tt) % p.frames;
+  const int ns = p.ns_per_utt ? p.ns_per_utt[b] : p.ns;
+  const int frames = 1 + ns / p.hop;                       // librosa center=True frame count
+  const int fr = (p.crop_start[b] + tt) % frames;          // tiling of short utterances (wsj0_2mix.py:118-123)
   const float* wav = p.wav[sig] + (long long)b * p.ns;
   float2* d = data + sig * N;
 
   for (int n = tx; n < N; n += nthr) {
     int pos = fr * p.hop - N / 2 + n;
     if (pos < 0) pos = -pos;
-    if (pos >= p.ns) pos = 2 * (p.ns - 1) - pos;
-    pos = max(0, min(p.ns - 1, pos));
+    if (pos >= ns) pos = 2 * (ns - 1) - pos;
+    pos = max(0, min(ns - 1, pos));
     const float v = wav[pos] * hann_periodic(n, N);
     d[__brev((unsigned)n) >> (32 - p.logN)] = make_float2(v, 0.f);
   }
@@ -221,7 +224,7 @@ extern "C" int onssen_stft_features(const float* wav_mix, const float* wav_s1, c
                                     int nsample, int n_fft, int hop, const int32_t* crop_start, int T,
                                     float* feature, float* mag_mix, float* mag_s1, float* mag_s2, float* cos_s1,
                                     float* cos_s2, float* ph_mix, float* ph_s1, float* ph_s2, float* feat_max,
-                                    void* stream) {
+                                    const int32_t* nsample_per_utt, void* stream) {
   if (!wav_mix || !crop_start || B <= 0 || T <= 0 || hop <= 0) return ONSSEN_ERR_ARG;
   if (n_fft < 64 || n_fft > 2048 || (n_fft & (n_fft - 1))) return ONSSEN_ERR_UNSUPPORTED;
   if (nsample <= n_fft / 2) return ONSSEN_ERR_ARG;
@@ -230,8 +233,8 @@ extern "C" int onssen_stft_features(const float* wav_mix, const float* wav_s1, c
   StftParams p;
   p.wav[0] = wav_mix; p.wav[1] = wav_s1; p.wav[2] = wav_s2;
   p.crop_start = crop_start;
+  p.ns_per_utt = nsample_per_utt;
   p.B = B; p.ns = nsample; p.N = n_fft; p.logN = ilog2(n_fft); p.hop = hop; p.T = T; p.F = n_fft / 2 + 1;
-  p.frames = 1 + nsample / hop;
   p.nsig = need_s ? 3 : 1;
   p.feature = feature;
   p.mag[0] = mag_mix; p.mag[1] = mag_s1; p.mag[2] = mag_s2;

@@ -27,15 +27,16 @@ def num_crop_starts(nsample, hop_size, frame_length):
 
 
 def featurize_batch(wav_mix, wav_s1, wav_s2, model_name, window_size, hop_size, frame_length, db_threshold,
-                    crop_start=None, label_dtype=torch.float32):
+                    crop_start=None, label_dtype=torch.float32, lengths=None):
     """wav_* (B, nsample) fp32 CUDA tensors -> (input_list, label_list) with the reference's per-model layout
     (wsj0_2mix.py:137-152). crop_start: int32 (B,) or None (drawn with numpy's global RNG like the reference)."""
     B, ns = wav_mix.shape
     if crop_start is None:
-        hi = num_crop_starts(ns, hop_size, frame_length)
-        crop_start = torch.from_numpy(np.random.randint(hi, size=B).astype(np.int32))
+        lens = [ns] * B if lengths is None else [int(v) for v in lengths]
+        crop_start = torch.from_numpy(np.array(
+            [np.random.randint(num_crop_starts(n, hop_size, frame_length)) for n in lens], dtype=np.int32))
     o = _lib.stft_features(wav_mix, wav_s1, wav_s2, window_size, hop_size, crop_start, frame_length,
-                           _WANT[model_name])
+                           _WANT[model_name], lengths=lengths)
     one_hot = _lib.one_hot_vad(o["feature"], o["mag_s1"], o["mag_s2"], o["feat_max"], db_threshold, label_dtype)
     if model_name == "dc":
         return [o["feature"]], [one_hot, o["mag_mix"]]

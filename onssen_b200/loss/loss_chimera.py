@@ -6,15 +6,19 @@ from .. import _lib
 from .loss_dc import loss_dc
 
 
-def _pit(mask_A, mask_B, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None):
-    # the reference's masks are strided views masks[..., k] of one (B,T,F,S) tensor; accept both layouts
+def _mask_args(mask_A, mask_B):
+    """the reference's masks are strided views masks[..., k] of one (B,T,F,S) tensor; accept both layouts"""
     if mask_A.is_contiguous() and mask_B.is_contiguous():
-        stride = 1
-    else:
-        stride = mask_A.stride(-1)
-        exp = (mask_A.shape[1] * mask_A.shape[2] * stride, mask_A.shape[2] * stride, stride)
-        if tuple(mask_A.stride()) != exp or tuple(mask_B.stride()) != exp:
-            mask_A, mask_B, stride = mask_A.contiguous(), mask_B.contiguous(), 1
+        return mask_A, mask_B, 1
+    stride = mask_A.stride(-1)
+    exp = (mask_A.shape[1] * mask_A.shape[2] * stride, mask_A.shape[2] * stride, stride)
+    if tuple(mask_A.stride()) != exp or tuple(mask_B.stride()) != exp:
+        return mask_A.contiguous(), mask_B.contiguous(), 1
+    return mask_A, mask_B, stride
+
+
+def _pit(mask_A, mask_B, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None):
+    mask_A, mask_B, stride = _mask_args(mask_A, mask_B)
     c = lambda t: None if t is None else t.float().contiguous()
     out, _ = _lib.loss_pit_l1_fwd(mask_A, mask_B, stride, c(mag_mix), c(mag_s1), c(mag_s2), c(cos_s1), c(cos_s2))
     return out

@@ -65,14 +65,20 @@ def require_no_grad(module_name, *tensors):
 
 def blstm_forward(rnn, cache, x, training, want_f32, want_f16, use_tensor_cores=True):
     """x (B,T,I) fp32 CUDA. Returns (y_h fp16 [T*B][2Hp] or None, y_f fp32 [T*B][2Hp] or None)."""
+    B, T, _ = x.shape
+    return blstm_forward_packed(rnn, cache, _lib.pack_input_f16(x.contiguous()), B, T, training, want_f32,
+                                want_f16, use_tensor_cores)
+
+
+def blstm_forward_packed(rnn, cache, a, B, T, training, want_f32, want_f16, use_tensor_cores=True):
+    """Same, from an already packed time-major fp16 input a [T*B][Kp]."""
     assert rnn.bidirectional and rnn.batch_first and rnn.proj_size == 0
-    B, T, I = x.shape
     H, L = rnn.hidden_size, rnn.num_layers
     Hp = _lib.hp_of(H)
     M = T * B
+    x = a
     params = [p for l in range(L) for d in lstm_layer_params(rnn, l) for p in d]
     packed = cache.get(params, lambda: pack_lstm(rnn))
-    a = _lib.pack_input_f16(x.contiguous())
     gates = torch.empty(M, 8 * Hp, device=x.device, dtype=torch.float32)
     ws = _lib.blstm_rec_workspace(B, H, x.device)
     y_h = y_f = None

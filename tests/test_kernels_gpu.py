@@ -68,7 +68,7 @@ def test_pack_layouts(lib):
     wih_p, whh_p, bias_p = lib.lstm_pack_layer(wf, wr, H, I, False, 0)
     assert wih_p.shape == (8 * Hp, 64)
     wih = wih_p.cpu().numpy().astype(np.float32)
-    whh = whh_p.cpu().numpy().astype(np.float32).reshape(2, Hp // 32, Hp // 8, 128, 8)
+    whh = whh_p.cpu().numpy().astype(np.float32).reshape(2, Hp // 32, 128, Hp)
     bias = bias_p.cpu().numpy()
     for d, w in enumerate((wf, wr)):
         w_ih, w_hh, b_ih, b_hh = [t.cpu().numpy() for t in w]
@@ -79,7 +79,7 @@ def test_pack_layouts(lib):
                 if u < H:
                     np.testing.assert_array_equal(wih[n, :I], w_ih[gate * H + u].astype(np.float16).astype(np.float32))
                     assert (wih[n, I:] == 0).all()
-                    row = whh[d, rb, :, 4 * ul + gate, :].reshape(-1)
+                    row = whh[d, rb, 4 * ul + gate, :]
                     np.testing.assert_array_equal(row[:H], w_hh[gate * H + u].astype(np.float16).astype(np.float32))
                     assert (row[H:] == 0).all()
                     assert bias[n] == b_ih[gate * H + u] + b_hh[gate * H + u]

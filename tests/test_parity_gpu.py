@@ -44,7 +44,7 @@ def test_deep_clustering_vs_reference_fixture(cuda_device, name, tc):
         np.testing.assert_allclose(loss.cpu().numpy(), g["loss_eval"], rtol=20 * LOSS_RTOL)  # tiny T*F: little averaging
         model.train()
         emb_t, = model([cu(g["feature"])])
-        np.testing.assert_allclose(emb_t.cpu().numpy(), g["emb_train"], atol=EMB_ATOL)
+        np.testing.assert_allclose(emb_t.cpu().numpy(), g["emb_train"], atol=2 * EMB_ATOL)  # B*T=48 samples: batch stats amplify rounding
         np.testing.assert_allclose(model.bn.running_mean.cpu().numpy(), g["bn_rm_after"], atol=1e-4)
         np.testing.assert_allclose(model.bn.running_var.cpu().numpy(), g["bn_rv_after"], rtol=1e-3)
     # the loss kernel alone, on the reference's own embedding: fp32 arithmetic, tight tolerance
