@@ -302,9 +302,9 @@ int dispatch_dc(const float* emb, const void* label, const float* mag, int B, in
   *fast = 1;
   if (S == 2 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0) {
     switch (D) {
-      // 10x10 register tiles: 100 FMA per 10 64-bit smem loads -> FMA-bound instead of smem-bound
-      case 20: return launch_dc_fast<20, 10, LT>(emb, label, mag, B, N, scratch, s);
-      case 40: return launch_dc_fast<40, 10, LT>(emb, label, mag, B, N, scratch, s);
+      // 5x5 register tiles (measured on B200 at cfg2: 321 us; 10x10 tiles drop to 1 CTA/SM and take 636 us)
+      case 20: return launch_dc_fast<20, 5, LT>(emb, label, mag, B, N, scratch, s);
+      case 40: return launch_dc_fast<40, 5, LT>(emb, label, mag, B, N, scratch, s);
       case 8: return launch_dc_fast<8, 4, LT>(emb, label, mag, B, N, scratch, s);
       case 16: return launch_dc_fast<16, 4, LT>(emb, label, mag, B, N, scratch, s);
       case 32: return launch_dc_fast<32, 4, LT>(emb, label, mag, B, N, scratch, s);

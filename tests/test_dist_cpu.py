@@ -1,0 +1,85 @@
+"""world_size-2 gloo tests (CPU) of the batch-sharding host logic used by bench.py --gpus N / the loaders."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from onssen_b200.utils import dist as D
+    assert D.env_rank_world() == (rank, world, rank)
+    # utterance shards: disjoint, contiguous, cover everything
+    n = 37
+    lo, hi = D.shard_range(n, rank, world)
+    owned = torch.zeros(n)
+    owned[lo:hi] = 1
+    dist.all_reduce(owned)
+    assert torch.equal(owned, torch.ones(n))
+    # timing protocol: every rank sees the slowest rank's time
+    t = D.max_over_ranks(1.0 + rank)
+    assert t == float(world)
+    # global loss mean from per-shard vectors == single-process value of mean over the (B,B) outer product
+    rng = np.random.RandomState(0)
+    l_all = torch.from_numpy(rng.uniform(0.1, 1, n).astype(np.float32))
+    m_all = torch.from_numpy(rng.uniform(10, 20, n).astype(np.float32))
+    want = float((l_all[None, :] * m_all[:, None]).double().mean())
+    got = D.global_loss_mean(l_all[lo:hi], m_all[lo:hi])
+    assert abs(got - want) < 1e-9 * abs(want) + 1e-9, (got, want)
+    # and it differs from the naive mean of per-shard means (why the 4-scalar reduction exists)
+    naive = D.sum_over_ranks(float((l_all[lo:hi][None, :] * m_all[lo:hi][:, None]).double().mean())) / world
+    ret[rank] = (got, naive, want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharding_and_reductions_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert len(ret) == world
+    got0, naive0, want0 = ret[0]
+    assert abs(got0 - ret[1][0]) < 1e-12
+    assert abs(naive0 - want0) > 1e-6          # the naive per-shard mean is NOT the global value
+
+
+def test_loader_file_sharding(tmp_path):
+    from scipy.io import wavfile
+    from onssen_b200.data import wsj0_2mix_dataloader
+    root = tmp_path / "wav8k" / "min" / "tr"
+    for sub in ("mix", "s1", "s2"):
+        (root / sub).mkdir(parents=True)
+    rng = np.random.RandomState(0)
+    for i in range(5):
+        n = 4000 + 100 * i
+        for sub in ("mix", "s1", "s2"):
+            wavfile.write(str(root / sub / f"utt{i}.wav"), 8000, (rng.standard_normal(n) * 3000).astype(np.int16))
+    fo = dict(data_path=str(tmp_path), batch_size=2, frame_length=40, sampling_rate=8000, window_size=256, hop_size=64,
+              db_threshold=40)
+    full = wsj0_2mix_dataloader("dc", fo, "tr")
+    assert len(full.file_list) == 5 and len(full) == 3
+    parts = [wsj0_2mix_dataloader("dc", fo, "tr", rank=r, world_size=2).file_list for r in range(2)]
+    assert sorted(parts[0] + parts[1]) == full.file_list and not set(parts[0]) & set(parts[1])
+    (mix, s1, s2), lengths = full._load(full.file_list[:2])
+    assert mix.shape == (2, 4100) and lengths.tolist() == [4000, 4100]
+    assert float(mix[0, 4000:].abs().max()) == 0.0           # zero padded to the batch pitch

@@ -1,0 +1,80 @@
+"""End-to-end plugin pipeline on the device: wav files -> loader (device featurizer) -> model -> loss,
+validation/checkpoint through `trainer`, evaluation through `tester_*` (masked iSTFT)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import onssen_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_corpus(tmp_path, n_utt=3):
+    from scipy.io import wavfile
+    utts = []
+    for part in ("tr", "cv", "tt"):
+        for sub in ("mix", "s1", "s2"):
+            os.makedirs(tmp_path / "wav8k" / "min" / part / sub, exist_ok=True)
+    for i in range(n_utt):
+        ns = 9000 + 640 * i
+        mix, s1, s2 = O.synth_utterance(i, ns)
+        q = lambda x: np.clip(np.round(x * 32768), -32768, 32767).astype(np.int16)
+        for part in ("tr", "cv", "tt"):
+            for sub, x in (("mix", mix), ("s1", s1), ("s2", s2)):
+                wavfile.write(str(tmp_path / "wav8k" / "min" / part / sub / f"u{i}.wav"), 8000, q(x))
+        utts.append(tuple(q(x).astype(np.float32) / 32768 for x in (mix, s1, s2)))
+    return utts
+
+
+def test_loader_matches_oracle_featurizer(cuda_device, tmp_path):
+    import onssen_b200 as ob
+    utts = _make_corpus(tmp_path)
+    fo = dict(data_path=str(tmp_path), batch_size=3, frame_length=100, sampling_rate=8000, window_size=256, hop_size=64,
+              db_threshold=40)
+    loader = ob.data.wsj0_2mix_dataloader("chimera++", fo, "cv", cuda_device)
+    loader.shuffle = False
+    np.random.seed(11)
+    inp, lab = next(iter(loader))
+    np.random.seed(11)   # the loader draws one np.random.randint per utterance, like wsj0_2mix.py:125
+    assert len(inp) == 1 and len(lab) == 6 and inp[0].shape == (3, 100, 129)
+    for b, (mix, s1, s2) in enumerate(utts):
+        start = np.random.randint(O.num_crop_starts(len(mix), 64, 100))
+        ri, rl = O.featurize(mix, s1, s2, 256, 64, 100, start, 40, "chimera++")
+        scale = rl[1].max()
+        np.testing.assert_allclose(lab[1][b].cpu().numpy(), rl[1], atol=3e-6 * scale)     # exact same frames
+        np.testing.assert_allclose(lab[2][b].cpu().numpy(), rl[2], atol=3e-6 * scale)
+        assert (lab[0][b].cpu().numpy() != rl[0]).any(-1).mean() < 1e-3
+
+
+def test_trainer_validate_and_tester_eval(cuda_device, tmp_path):
+    import onssen_b200 as ob
+    _make_corpus(tmp_path)
+    A = ob.utils.AttrDict
+    args = A({"model_name": "chimera", "device": str(cuda_device), "num_epoch": 1, "checkpoint_path": str(tmp_path / "ckpt"),
+              "feature_options": A(dict(data_path=str(tmp_path), batch_size=2, frame_length=100, sampling_rate=8000,
+                                        window_size=256, hop_size=64, db_threshold=40)),
+              "optimizer_options": A({"name": "adam", "lr": 1e-3}), "verbose": False})
+    torch.manual_seed(0)
+    args.model = ob.nn.chimera(129, 64, 2, 20).to(cuda_device)
+    args.train_loader = ob.data.wsj0_2mix_dataloader("chimera", args.feature_options, "tr", cuda_device)
+    args.valid_loader = ob.data.wsj0_2mix_dataloader("chimera", args.feature_options, "cv", cuda_device)
+    args.test_loader = ob.data.wsj0_2mix_dataloader("chimera", args.feature_options, "tt", cuda_device)
+    args.optimizer = ob.utils.build_optimizer(args.model.parameters(), args.optimizer_options)
+    args.loss_fn = ob.loss.loss_chimera_msa
+    tr = ob.utils.trainer(args)
+    v = tr.validate(0)
+    assert np.isfinite(v) and os.path.exists(tmp_path / "ckpt" / "final.mdl")
+    saved = torch.load(tmp_path / "ckpt" / "final.mdl", weights_only=False)
+    assert set(saved) == {"model", "epoch", "optimizer", "cv_loss", "early_stop_count"}     # train.py:111-122
+    assert "rnn.weight_hh_l1_reverse" in saved["model"] and "fc_mi.bias" in saved["model"]
+    sdr = ob.utils.tester_chimera(args).eval()
+    assert np.isfinite(sdr)
+    # eval labels: stft_r, stft_i, sig_ref and an all-ones mask reproduces the mixture through the device iSTFT
+    inp, lab = next(iter(args.test_loader))
+    ones = torch.ones(1, 1, *lab[0].shape[1:], device=cuda_device)
+    t = ob.utils.tester_chimera(args)
+    rec = t.masked_istft(lab[0], lab[1], ones, lab[2].shape[2])
+    mix = lab[2][0].sum(0)
+    assert (rec[0, 0] - mix).abs().max().item() < 2e-4 * mix.abs().max().item() + 1e-4   # s1+s2 == mix up to int16 rounding
