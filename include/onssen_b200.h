@@ -170,6 +170,14 @@ int onssen_loss_dc_num_chunks(int N);
 int onssen_loss_dc_fwd(const float* emb, const void* label, int label_dtype, const float* mag, int B, int N,
                        int D, int S, float* loss_bb, float* l, float* mag_sum, float* scratch, void* stream);
 
+/* Backward of onssen_loss_dc_fwd w.r.t. the embedding (autograd of loss_dc.py:24-44; labels and mag_mix carry no
+ * gradient, mag_mix is detached at :25). summed_record = the per-utterance summed Gram record the forward left
+ * at scratch + B*nchunk*(D*D+D*S+S*S+4) floats; g_bb [B][B] = upstream gradient of the (B,B) result;
+ * d_emb [B][N][D]. Supported for S == 2, D % 4 == 0 (the forward's fast layout). */
+int onssen_loss_dc_bwd(const float* emb, const void* label, int label_dtype, const float* mag,
+                       const float* summed_record, const float* g_bb, int B, int N, int D, int S, float* d_emb,
+                       void* stream);
+
 /* PIT L1 mask-inference loss for two speakers (replaces the mask part of loss_chimera_msa/psa,
  * onssen/loss/loss_chimera.py:25-29,53-57): per utterance
  *   min( L1(mA*mix - t1) + L1(mB*mix - t2),  L1(mB*mix - t1) + L1(mA*mix - t2) )
@@ -179,6 +187,58 @@ int onssen_loss_dc_fwd(const float* emb, const void* label, int label_dtype, con
 int onssen_loss_pit_l1_fwd(const float* mask_a, const float* mask_b, long long mask_stride, const float* mag_mix,
                            const float* mag_s1, const float* mag_s2, const float* cos_s1, const float* cos_s2,
                            int B, int N, float* out, int32_t* perm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training path: backward of the deep-clustering stack (autograd of onssen/nn/deep_clustering.py:34-42 as driven
+ * by loss_avg.backward() at onssen/utils/train.py:82).  fp32 gradients feed the fp16 tensor-core GEMMs through a
+ * power-of-two scale (scale2 = {2^k, 2^-k} on the device) so that nothing underflows.
+ */
+/* onssen_gemm_f16 with two extras: out_scale (device scalar multiplied into the accumulators, NULL = 1) and, for
+ * epi 3, inv_norm [output rows][N/group] = 1/max(||z||, 1e-12) of every normalised group (NULL to skip). */
+int onssen_gemm_f16_ex(const void* A, const void* W, const float* bias, float* out, int M, int N, int K,
+                       long long lda, long long ldw, long long ld_out, int epi, int group, int remap_inner,
+                       int remap_outer, const float* out_scale, float* inv_norm, void* stream);
+/* scale2[0] = 2^k with amax(x) * 2^k ~ target, scale2[1] = 2^-k. scratch_u32: 4 bytes. */
+int onssen_amax_scale(const float* x, long long n, float target, void* scratch_u32, float* scale2, void* stream);
+int onssen_scale_from_amax_bits(const void* amax_bits_u32, float target, float* scale2, void* stream);
+/* src fp32 [R][C] (pitch ld) * scale2[0] -> out_n fp16 [R][Cp] and/or out_t fp16 [C][Rp] (zero padded). */
+int onssen_cast_transpose_f16(const float* src, int R, int C, long long ld, const float* scale2, void* out_n,
+                              int Cp, void* out_t, int Rp, void* stream);
+/* fp16 src [R][*] (pitch ld), columns [col0, col0+ncol) -> out_t fp16 [ncol][Rp], out_t[c][r] = src[r-shift][col0+c]
+ * (zero outside): transposed and time-shifted copy for the W_hh weight gradient (h_{t-1} against dG_t). */
+int onssen_transpose_shift_f16(const void* src, int R, long long ld, int col0, int ncol, int shift, void* out_t,
+                               int Rp, void* stream);
+size_t onssen_colsum_scratch_bytes(int R, int C);
+/* out[c] = mult * sum_r x[r][c] (bias gradients), deterministic two-stage reduction. */
+int onssen_colsum(const float* x, int R, int C, long long ld, float mult, float* out, void* scratch, void* stream);
+/* F.normalize backward (deep_clustering.py:41): d_emb, emb batch-first (B,T,F,D), inv_norm (B,T,F) ->
+ * dz time-major [T*B][F*D] fp32; amax_bits_u32 receives the bit pattern of max|dz|. */
+int onssen_normalize_bwd(const float* d_emb, const float* emb, const float* inv_norm, int B, int T, int F, int D,
+                         float* dz, void* amax_bits_u32, void* stream);
+size_t onssen_bn_backward_scratch_bytes(int M, int H);
+/* BatchNorm1d backward (batch statistics) on the padded layout: d_out, y, d_y [M][2Hp] fp32; save_mean /
+ * save_invstd from onssen_bn_forward_f16; d_gamma, d_beta [2H]. */
+int onssen_bn_backward(const float* d_out, const float* y, int M, int H, const float* gamma, const float* save_mean,
+                       const float* save_invstd, float* d_y, float* d_gamma, float* d_beta, void* scratch,
+                       void* stream);
+/* Inverse of onssen_pack_linear_f16 / onssen_lstm_pack_layer for fp32 gradient buffers:
+ * gp [N][Kp] -> g [N][K];  gp [2*4Hp][Kp] rows of `dir` -> g [4H][K] in PyTorch gate order. */
+int onssen_unpack_linear_grad(const float* gp, int N, int K, int in_is_blstm, int Hin, int Kp, float* g, void* stream);
+int onssen_unpack_lstm_grad(const float* gp, int H, int K, int in_is_blstm, int Hin, int Kp, int dir, float* g,
+                            void* stream);
+/* W_hh (both directions, fp32 [4H][H]) -> fp16 [2][Hp][4Hp]: transposed, permuted gate rows, zero padded. */
+int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, int H, void* out, void* stream);
+/* Forward recurrence that also saves the BPTT state: the activated gates overwrite gates_inout in place, c_out
+ * [T*B][2Hp] fp32, h_raw [T*B][2Hp] fp16 = h before dropout (NULL when dropout_p == 0: use y_h). */
+int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
+                               float* c_out, void* h_raw, float dropout_p, unsigned long long seed,
+                               unsigned long long offset, void* workspace, size_t workspace_bytes, void* stream);
+/* BPTT over one layer, both directions (one launch per step). act_gates: saved activations, overwritten with the
+ * fp32 pre-activation gradients dG; dg16 receives dG * scale2[0] in fp16; dy = gradient w.r.t. the layer output
+ * (the dropout mask is re-derived from seed/offset); dc_carry [2][B][Hp] scratch. */
+int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
+                         float* dc_carry, const float* scale2, int B, int T, int H, float dropout_p,
+                         unsigned long long seed, unsigned long long offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Enhancement / phase-network variants of the path

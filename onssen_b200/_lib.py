@@ -44,7 +44,24 @@ _SIGNATURES = {
     "onssen_loss_dc_num_chunks": (c_int, [c_int]),
     "onssen_loss_dc_fwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                                    c_vp]),
+    "onssen_loss_dc_bwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "onssen_loss_pit_l1_fwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 5 + [c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_gemm_f16_ex": (c_int, [c_vp] * 4 + [c_int] * 3 + [c_ll] * 3 + [c_int] * 4 + [c_vp, c_vp, c_vp]),
+    "onssen_amax_scale": (c_int, [c_vp, c_ll, c_f, c_vp, c_vp, c_vp]),
+    "onssen_scale_from_amax_bits": (c_int, [c_vp, c_f, c_vp, c_vp]),
+    "onssen_cast_transpose_f16": (c_int, [c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
+    "onssen_transpose_shift_f16": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "onssen_colsum_scratch_bytes": (c_sz, [c_int, c_int]),
+    "onssen_colsum": (c_int, [c_vp, c_int, c_int, c_ll, c_f, c_vp, c_vp, c_vp]),
+    "onssen_normalize_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_bn_backward_scratch_bytes": (c_sz, [c_int, c_int]),
+    "onssen_bn_backward": (c_int, [c_vp, c_vp, c_int, c_int] + [c_vp] * 8),
+    "onssen_unpack_linear_grad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "onssen_unpack_lstm_grad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "onssen_lstm_pack_whh_t": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
+    "onssen_blstm_rec_fwd_train": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_ull, c_ull,
+                                           c_vp, c_sz, c_vp]),
+    "onssen_blstm_rec_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
     "onssen_mul_pack_f16": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_int, c_vp]),
     "onssen_pack_phase_input_f16": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_add_l2norm_pairs": (c_int, [c_vp, c_vp, c_ll, c_vp, c_vp]),
@@ -62,7 +79,7 @@ REC_EVENTS = None
 _KERNELS_PER_CALL = {"onssen_stft_features": 2, "onssen_one_hot_vad": 1, "onssen_istft_masked": 2,
                      "onssen_pack_input_f16": 1, "onssen_lstm_pack_layer": 3, "onssen_pack_linear_f16": 1,
                      "onssen_gemm_f16": 1, "onssen_blstm_rec_fwd": 1, "onssen_bn_forward_f16": 3,
-                     "onssen_cast_f16": 1, "onssen_loss_dc_fwd": 4, "onssen_loss_pit_l1_fwd": 1,
+                     "onssen_cast_f16": 1, "onssen_loss_dc_fwd": 4, "onssen_loss_dc_bwd": 1, "onssen_loss_pit_l1_fwd": 1,
                      "onssen_mul_pack_f16": 1, "onssen_pack_phase_input_f16": 1, "onssen_add_l2norm_pairs": 1,
                      "onssen_loss_l1_psa_fwd": 1, "onssen_loss_mse_fwd": 2, "onssen_loss_phase_cos_fwd": 1}
 
@@ -286,7 +303,7 @@ def cast_f16(y):
 
 
 # ------------------------------------------------------------------------------------------------ losses
-def loss_dc_fwd(emb, label, mag):
+def loss_dc_fwd(emb, label, mag, return_record=False):
     """emb (B,N,D) fp32, label (B,N,S) f32/f64/u8, mag (B,N) fp32 -> (loss_bb (B,B), l (B,), mag_sum (B,))"""
     lib = load()
     B, N, D = emb.shape
@@ -303,7 +320,22 @@ def loss_dc_fwd(emb, label, mag):
                                 _DT[label.dtype], _p(_req(mag, torch.float32, "mag_mix")), B, N, D, S, _p(loss_bb),
                                 _p(l), _p(msum), _p(scratch), _stream())
     _check(rc, "onssen_loss_dc_fwd")
+    if return_record:
+        rmax = D * D + D * S + S * S + 4
+        return loss_bb, l, msum, scratch[B * nchunk * rmax:]
     return loss_bb, l, msum
+
+
+def loss_dc_bwd(emb, label, mag, summed_record, g_bb):
+    lib = load()
+    B, N, D = emb.shape
+    S = label.shape[-1]
+    d_emb = torch.empty_like(emb)
+    rc = lib.onssen_loss_dc_bwd(_p(_req(emb, torch.float32)), _p(_req(label)), _DT[label.dtype],
+                                _p(_req(mag, torch.float32)), _p(summed_record),
+                                _p(_req(g_bb.float().contiguous(), torch.float32)), B, N, D, S, _p(d_emb), _stream())
+    _check(rc, "onssen_loss_dc_bwd")
+    return d_emb
 
 
 def loss_pit_l1_fwd(mask_a, mask_b, mask_stride, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None):
@@ -381,3 +413,128 @@ def loss_phase_cos_fwd(pa, pb, s1, s2, mag, perm):
                                        _p(_req(perm, torch.int32)), B, N, _p(out), _stream())
     _check(rc, "onssen_loss_phase_cos_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training path
+def pad64(n):
+    return (n + 63) // 64 * 64
+
+
+def gemm_f16_ex(A, W, bias, out, M, N, K, ld_out, epi=0, group=0, remap_inner=0, remap_outer=0, out_scale=None,
+                inv_norm=None):
+    lib = load()
+    rc = lib.onssen_gemm_f16_ex(_p(_req(A, torch.float16)), _p(_req(W, torch.float16)), _p(bias), _p(out), M, N, K,
+                                A.stride(0), W.stride(0), ld_out, epi, group, remap_inner, remap_outer,
+                                _p(out_scale), _p(inv_norm), _stream())
+    _check(rc, "onssen_gemm_f16")
+    return out
+
+
+def amax_scale(x, target=1024.0):
+    lib = load()
+    scratch = torch.empty(1, device=x.device, dtype=torch.int32)
+    scale2 = torch.empty(2, device=x.device, dtype=torch.float32)
+    _check(lib.onssen_amax_scale(_p(_req(x, torch.float32)), x.numel(), float(target), _p(scratch), _p(scale2),
+                                 _stream()), "onssen_amax_scale")
+    return scale2
+
+
+def cast_transpose_f16(src, scale2, want_n=True, want_t=True):
+    """src fp32 [R][C] -> (fp16 [R][pad64(C)] or None, fp16 [C][pad64(R)] or None), both times scale2[0]."""
+    lib = load()
+    R, C = src.shape
+    Cp, Rp = pad64(C), pad64(R)
+    out_n = torch.empty(R, Cp, device=src.device, dtype=torch.float16) if want_n else None
+    out_t = torch.empty(C, Rp, device=src.device, dtype=torch.float16) if want_t else None
+    rc = lib.onssen_cast_transpose_f16(_p(_req(src, torch.float32)), R, C, src.stride(0), _p(scale2), _p(out_n), Cp,
+                                       _p(out_t), Rp, _stream())
+    _check(rc, "onssen_cast_transpose_f16")
+    return out_n, out_t
+
+
+def transpose_shift_f16(src, col0, ncol, shift=0):
+    lib = load()
+    R = src.shape[0]
+    Rp = pad64(R)
+    out = torch.empty(ncol, Rp, device=src.device, dtype=torch.float16)
+    rc = lib.onssen_transpose_shift_f16(_p(_req(src, torch.float16)), R, src.stride(0), col0, ncol, shift, _p(out), Rp,
+                                        _stream())
+    _check(rc, "onssen_transpose_shift_f16")
+    return out
+
+
+def colsum(x, mult=1.0):
+    lib = load()
+    R, C = x.shape
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(lib.onssen_colsum_scratch_bytes(R, C), device=x.device, dtype=torch.uint8)
+    _check(lib.onssen_colsum(_p(_req(x, torch.float32)), R, C, x.stride(0), float(mult), _p(out), _p(scratch), _stream()),
+           "onssen_colsum")
+    return out
+
+
+def normalize_bwd(d_emb, emb, inv_norm):
+    lib = load()
+    B, T, F, D = emb.shape
+    dz = torch.empty(T * B, F * D, device=emb.device, dtype=torch.float32)
+    amax = torch.empty(1, device=emb.device, dtype=torch.int32)
+    rc = lib.onssen_normalize_bwd(_p(_req(d_emb, torch.float32)), _p(_req(emb, torch.float32)),
+                                  _p(_req(inv_norm, torch.float32)), B, T, F, D, _p(dz), _p(amax), _stream())
+    _check(rc, "onssen_normalize_bwd")
+    scale2 = torch.empty(2, device=emb.device, dtype=torch.float32)
+    _check(lib.onssen_scale_from_amax_bits(_p(amax), 1024.0, _p(scale2), _stream()), "onssen_scale_from_amax_bits")
+    return dz, scale2
+
+
+def bn_backward(d_out, y, M, H, gamma, save_mean, save_invstd):
+    lib = load()
+    d_y = torch.empty_like(y)
+    dg = torch.empty(2 * H, device=y.device, dtype=torch.float32)
+    db = torch.empty(2 * H, device=y.device, dtype=torch.float32)
+    scratch = torch.empty(lib.onssen_bn_backward_scratch_bytes(M, H), device=y.device, dtype=torch.uint8)
+    rc = lib.onssen_bn_backward(_p(_req(d_out, torch.float32)), _p(_req(y, torch.float32)), M, H, _p(gamma),
+                                _p(save_mean), _p(save_invstd), _p(d_y), _p(dg), _p(db), _p(scratch), _stream())
+    _check(rc, "onssen_bn_backward")
+    return d_y, dg, db
+
+
+def unpack_linear_grad(gp, N, K, in_is_blstm, Hin=0):
+    lib = load()
+    g = torch.empty(N, K, device=gp.device, dtype=torch.float32)
+    _check(lib.onssen_unpack_linear_grad(_p(_req(gp, torch.float32)), N, K, int(in_is_blstm), Hin, gp.stride(0), _p(g),
+                                         _stream()), "onssen_unpack_linear_grad")
+    return g
+
+
+def unpack_lstm_grad(gp, H, K, in_is_blstm, Hin, direction, Kp=None):
+    lib = load()
+    g = torch.empty(4 * H, K, device=gp.device, dtype=torch.float32)
+    kp = gp.stride(0) if Kp is None else Kp
+    _check(lib.onssen_unpack_lstm_grad(_p(gp), H, K, int(in_is_blstm), Hin, kp, direction, _p(g), _stream()),
+           "onssen_unpack_lstm_grad")
+    return g
+
+
+def lstm_pack_whh_t(w_hh_f, w_hh_r, H):
+    lib = load()
+    Hp = hp_of(H)
+    out = torch.empty(2, Hp, 4 * Hp, device=w_hh_f.device, dtype=torch.float16)
+    _check(lib.onssen_lstm_pack_whh_t(_p(_req(w_hh_f.detach(), torch.float32)), _p(_req(w_hh_r.detach(), torch.float32)),
+                                      H, _p(out), _stream()), "onssen_lstm_pack_whh_t")
+    return out
+
+
+def blstm_rec_fwd_train(gates, whh_p, B, T, H, y_h, y_f, c_out, h_raw, dropout_p, seed, offset, workspace):
+    lib = load()
+    rc = lib.onssen_blstm_rec_fwd_train(_p(_req(gates, torch.float32)), _p(whh_p), B, T, H, _p(y_h), _p(y_f), _p(c_out),
+                                        _p(h_raw), float(dropout_p), int(seed), int(offset), _p(workspace),
+                                        workspace.numel(), _stream())
+    _check(rc, "onssen_blstm_rec_fwd")
+
+
+def blstm_rec_bwd(act_gates, dg16, c, dy, whh_t, scale2, B, T, H, dropout_p, seed, offset):
+    lib = load()
+    dc = torch.zeros(2, B, hp_of(H), device=c.device, dtype=torch.float32)
+    rc = lib.onssen_blstm_rec_bwd(_p(act_gates), _p(dg16), _p(c), _p(_req(dy, torch.float32)), _p(whh_t), _p(dc),
+                                  _p(scale2), B, T, H, float(dropout_p), int(seed), int(offset), _stream())
+    _check(rc, "onssen_blstm_rec_bwd")

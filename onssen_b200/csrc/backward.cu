@@ -1,0 +1,340 @@
+// Backward-pass helpers of the training path (autograd of deep_clustering.py:34-42 + train.py:81-84):
+//   * amax -> power-of-two loss scale so fp32 gradients can feed the fp16 tensor-core GEMMs without underflow
+//   * scaled fp32 -> fp16 cast with an optional transposed (and time-shifted) copy: wgrad GEMMs contract over
+//     the row dimension M, so both operands are needed M-contiguous
+//   * F.normalize backward, BatchNorm1d backward, column sums (bias grads), gradient un-permutation / un-padding
+// All HBM-bound streaming / column-reduction kernels.
+#include "common.cuh"
+
+namespace onssen {
+namespace {
+
+inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+__global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));   // positive floats order as uints
+}
+
+// scale[0] = 2^k with amax * 2^k ~= target (k clamped), scale[1] = 2^-k
+__global__ void make_scale_kernel(const unsigned int* __restrict__ amax_bits, float target, float* __restrict__ scale) {
+  const float a = __uint_as_float(*amax_bits);
+  float k = 0.f;
+  if (a > 0.f && isfinite(a)) k = floorf(log2f(target / a));
+  k = fminf(fmaxf(k, -60.f), 60.f);
+  scale[0] = exp2f(k);
+  scale[1] = exp2f(-k);
+}
+
+// src fp32 [R][C] (row pitch ld) -> out_n fp16 [R][Cp] (zero padded) and/or out_t fp16 [C][Rp] (zero padded),
+// both multiplied by scale[0] (or 1).  32x32 smem tile transpose.
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ src, int R, int C, long long ld, const float* __restrict__ scale,
+                      __half* __restrict__ out_n, int Cp, __half* __restrict__ out_t, int Rp) {
+  __shared__ float tile[32][33];
+  const float sc = scale ? scale[0] : 1.0f;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    const float v = (r < R && c < C) ? src[(long long)r * ld + c] * sc : 0.f;
+    tile[i][tx] = v;
+    if (out_n != nullptr && r < R && c < Cp) out_n[(long long)r * Cp + c] = to_half_sat(v);
+  }
+  if (out_t == nullptr) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < Rp) out_t[(long long)c * Rp + r] = to_half_sat(tile[tx][i]);
+  }
+}
+
+// fp16 src [R][C] (pitch ld) -> out_t fp16 [C][Rp] with the rows shifted: out_t[c][r] = src[r - shift][c]
+// (zero outside [0,R)).  Only columns [col0, col0+ncol) are transposed (row c - col0 of out_t).
+__global__ void __launch_bounds__(256)
+transpose_shift_f16_kernel(const __half* __restrict__ src, int R, long long ld, int col0, int ncol, int shift,
+                           __half* __restrict__ out_t, int Rp) {
+  __shared__ __half tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;     // r0 indexes OUTPUT rows-of-src (after shift)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i - shift, c = c0 + tx;
+    tile[i][tx] = (r >= 0 && r < R && c < ncol) ? src[(long long)r * ld + col0 + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < ncol && r < Rp) out_t[(long long)c * Rp + r] = tile[tx][i];
+  }
+}
+
+// column sums of fp32 [R][C] (pitch ld) scaled by `mult`: two-stage, deterministic.
+constexpr int CS_ROWS = 256;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ x, int R, int C, long long ld, double* __restrict__ part) {
+  __shared__ double sp[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
+  double s = 0.0;
+  if (c < C)
+    for (int r = r0 + warp; r < r1; r += 8) s += (double)x[(long long)r * ld + c];
+  sp[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sp[w][lane];
+    part[(long long)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const double* __restrict__ part, int nchunk, int C, float mult,
+                                    float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t = 0.0;
+  for (int k = 0; k < nchunk; ++k) t += part[(long long)k * C + c];
+  out[c] = (float)t * mult;
+}
+
+// F.normalize backward + layout change: d_emb / emb are batch-first (B,T,F,D); dz is written time-major
+// [T*B][F*D] fp32:  dz = (de - e * <e,de>) * inv_norm.   One thread per (row, group).
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const float* __restrict__ d_emb, const float* __restrict__ emb,
+                     const float* __restrict__ inv_norm, int B, int T, int F, int D, float* __restrict__ dz,
+                     unsigned int* __restrict__ amax_bits) {
+  const long long total = (long long)B * T * F;
+  float am = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long bt = i / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float* e = emb + i * D;
+    const float* g = d_emb + i * D;
+    float dot = 0.f;
+    for (int k = 0; k < D; ++k) dot = fmaf(e[k], g[k], dot);
+    const float inv = inv_norm[i];
+    float* o = dz + ((long long)t * B + b) * ((long long)F * D) + (long long)f * D;
+    for (int k = 0; k < D; ++k) {
+      const float v = (g[k] - e[k] * dot) * inv;
+      o[k] = v;
+      am = fmaxf(am, fabsf(v));
+    }
+  }
+  am = warp_max(am);
+  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_uint(am));
+}
+
+// BatchNorm1d backward (train mode, batch statistics) on the padded channel layout.
+//   partial: per row chunk, sums of dA and dA*yhat per channel
+__global__ void __launch_bounds__(256)
+bn_bwd_partial_kernel(const float* __restrict__ d_out, const float* __restrict__ y, int M, int H, int Hp,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ part) {
+  __shared__ double s0[8][32], s1[8][32];
+  const int C = 2 * Hp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+  double a = 0.0, bq = 0.0;
+  if (c < C && (c % Hp) < H) {
+    const int j = (c / Hp) * H + (c % Hp);
+    const float mu = mean[j], is = invstd[j];
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const float g = d_out[(long long)r * C + c];
+      a += (double)g;
+      bq += (double)g * (double)((y[(long long)r * C + c] - mu) * is);
+    }
+  }
+  s0[warp][lane] = a;
+  s1[warp][lane] = bq;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { t0 += s0[w][lane]; t1 += s1[w][lane]; }
+    const int nchunk = gridDim.y;
+    part[(long long)blockIdx.y * C + c] = t0;
+    part[(long long)(nchunk + blockIdx.y) * C + c] = t1;
+  }
+}
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, int nchunk, int M, int H, int Hp,
+                                    const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                    float* __restrict__ d_gamma, float* __restrict__ d_beta,
+                                    float* __restrict__ coef /* [3][C]: a, b, c of dy = a*g + b*yhat + c */) {
+  const int C = 2 * Hp;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int u = c % Hp;
+  if (u >= H) { coef[c] = coef[C + c] = coef[2 * C + c] = 0.f; return; }
+  const int j = (c / Hp) * H + u;
+  double sg = 0.0, sgy = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    sg += part[(long long)k * C + c];
+    sgy += part[(long long)(nchunk + k) * C + c];
+  }
+  d_beta[j] = (float)sg;
+  d_gamma[j] = (float)sgy;
+  const float a = gamma[j] * invstd[j];
+  coef[c] = a;
+  coef[C + c] = -a * (float)(sgy / M);
+  coef[2 * C + c] = -a * (float)(sg / M);
+}
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, const float* __restrict__ y, long long M, int H,
+                                    int Hp, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ coef, float* __restrict__ d_y) {
+  const int C = 2 * Hp;
+  const long long total = M * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int u = c % Hp;
+    float v = 0.f;
+    if (u < H) {
+      const int j = (c / Hp) * H + u;
+      const float yh = (y[i] - mean[j]) * invstd[j];
+      v = fmaf(coef[c], d_out[i], fmaf(coef[C + c], yh, coef[2 * C + c]));
+    }
+    d_y[i] = v;
+  }
+}
+
+// padded/permuted gradient buffers -> PyTorch parameter layout (fp32), inverse of pack_* in pack.cu
+__global__ void unpack_linear_grad_kernel(const float* __restrict__ gp, int N, int K, int blstm, int Hin, int Hinp,
+                                          int Kp, float* __restrict__ g) {
+  const long long total = (long long)N * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % K);
+    const long long n = idx / K;
+    const int k = blstm ? (j / Hin) * Hinp + (j % Hin) : j;
+    g[idx] = gp[n * Kp + k];
+  }
+}
+__global__ void unpack_lstm_grad_kernel(const float* __restrict__ gp, int H, int Hp, int K, int blstm, int Hin,
+                                        int Hinp, int Kp, int dir, float* __restrict__ g) {
+  // g [4H][K] <- gp [2*4Hp][Kp] rows of `dir`;  source row gate*H+u  <->  packed row dir*4Hp + rb*128 + 4*ul + gate
+  const long long total = 4LL * H * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % K);
+    const int row = (int)(idx / K);
+    const int gate = row / H, u = row % H;
+    const int n = dir * 4 * Hp + (u >> 5) * 128 + 4 * (u & 31) + gate;
+    const int k = blstm ? (j / Hin) * Hinp + (j % Hin) : j;
+    g[idx] = gp[(long long)n * Kp + k];
+  }
+}
+
+}  // namespace
+}  // namespace onssen
+
+using namespace onssen;
+
+extern "C" int onssen_amax_scale(const float* x, long long n, float target, void* scratch_u32, float* scale2,
+                                 void* stream) {
+  if (!x || !scratch_u32 || !scale2 || n <= 0) return ONSSEN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(scratch_u32, 0, 4, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+  amax_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, n, (unsigned int*)scratch_u32);
+  make_scale_kernel<<<1, 1, 0, s>>>((const unsigned int*)scratch_u32, target, scale2);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_scale_from_amax_bits(const void* amax_bits_u32, float target, float* scale2, void* stream) {
+  if (!amax_bits_u32 || !scale2) return ONSSEN_ERR_ARG;
+  make_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned int*)amax_bits_u32, target, scale2);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_cast_transpose_f16(const float* src, int R, int C, long long ld, const float* scale2,
+                                         void* out_n, int Cp, void* out_t, int Rp, void* stream) {
+  if (!src || R <= 0 || C <= 0 || (!out_n && !out_t)) return ONSSEN_ERR_ARG;
+  if ((out_n && Cp < C) || (out_t && Rp < R)) return ONSSEN_ERR_ARG;
+  const int cmax = out_n ? (Cp > C ? Cp : C) : C;
+  const int rmax = out_t ? (Rp > R ? Rp : R) : R;
+  dim3 grid((cmax + 31) / 32, (rmax + 31) / 32);
+  cast_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, R, C, ld, scale2, (__half*)out_n, Cp,
+                                                                (__half*)out_t, Rp);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_transpose_shift_f16(const void* src, int R, long long ld, int col0, int ncol, int shift,
+                                          void* out_t, int Rp, void* stream) {
+  if (!src || !out_t || R <= 0 || ncol <= 0 || Rp < R) return ONSSEN_ERR_ARG;
+  dim3 grid((ncol + 31) / 32, (Rp + 31) / 32);
+  transpose_shift_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, R, ld, col0, ncol, shift,
+                                                                     (__half*)out_t, Rp);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" size_t onssen_colsum_scratch_bytes(int R, int C) {
+  return (size_t)((R + CS_ROWS - 1) / CS_ROWS) * C * sizeof(double) * 2;
+}
+
+extern "C" int onssen_colsum(const float* x, int R, int C, long long ld, float mult, float* out, void* scratch,
+                             void* stream) {
+  if (!x || !out || !scratch || R <= 0 || C <= 0) return ONSSEN_ERR_ARG;
+  const int nchunk = (R + CS_ROWS - 1) / CS_ROWS;
+  cudaStream_t s = (cudaStream_t)stream;
+  colsum_partial_kernel<<<dim3((C + 31) / 32, nchunk), 256, 0, s>>>(x, R, C, ld, (double*)scratch);
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>((const double*)scratch, nchunk, C, mult, out);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_normalize_bwd(const float* d_emb, const float* emb, const float* inv_norm, int B, int T,
+                                    int F, int D, float* dz, void* amax_bits_u32, void* stream) {
+  if (!d_emb || !emb || !inv_norm || !dz || !amax_bits_u32) return ONSSEN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(amax_bits_u32, 0, 4, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+  normalize_bwd_kernel<<<grid_for((long long)B * T * F, 256), 256, 0, s>>>(d_emb, emb, inv_norm, B, T, F, D, dz,
+                                                                           (unsigned int*)amax_bits_u32);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_bn_backward(const float* d_out, const float* y, int M, int H, const float* gamma,
+                                  const float* save_mean, const float* save_invstd, float* d_y, float* d_gamma,
+                                  float* d_beta, void* scratch, void* stream) {
+  if (!d_out || !y || !gamma || !save_mean || !save_invstd || !d_y || !d_gamma || !d_beta || !scratch)
+    return ONSSEN_ERR_ARG;
+  const int Hp = hp_of(H), C = 2 * Hp;
+  const int nchunk = (M + CS_ROWS - 1) / CS_ROWS;
+  double* part = (double*)scratch;
+  float* coef = (float*)(part + 2LL * nchunk * C);
+  cudaStream_t s = (cudaStream_t)stream;
+  bn_bwd_partial_kernel<<<dim3((C + 31) / 32, nchunk), 256, 0, s>>>(d_out, y, M, H, Hp, save_mean, save_invstd, part);
+  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, nchunk, M, H, Hp, gamma, save_invstd, d_gamma, d_beta,
+                                                      coef);
+  bn_bwd_apply_kernel<<<grid_for((long long)M * C, 256), 256, 0, s>>>(d_out, y, M, H, Hp, save_mean, save_invstd,
+                                                                      coef, d_y);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" size_t onssen_bn_backward_scratch_bytes(int M, int H) {
+  const int C = 2 * hp_of(H);
+  return (size_t)2 * ((M + CS_ROWS - 1) / CS_ROWS) * C * sizeof(double) + (size_t)3 * C * sizeof(float);
+}
+
+extern "C" int onssen_unpack_linear_grad(const float* gp, int N, int K, int in_is_blstm, int Hin, int Kp, float* g,
+                                         void* stream) {
+  if (!gp || !g || N <= 0 || K <= 0) return ONSSEN_ERR_ARG;
+  unpack_linear_grad_kernel<<<grid_for((long long)N * K, 256), 256, 0, (cudaStream_t)stream>>>(
+      gp, N, K, in_is_blstm, Hin, in_is_blstm ? hp_of(Hin) : 0, Kp, g);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_unpack_lstm_grad(const float* gp, int H, int K, int in_is_blstm, int Hin, int Kp, int dir,
+                                       float* g, void* stream) {
+  if (!gp || !g || H <= 0 || K <= 0 || dir < 0 || dir > 1) return ONSSEN_ERR_ARG;
+  unpack_lstm_grad_kernel<<<grid_for(4LL * H * K, 256), 256, 0, (cudaStream_t)stream>>>(
+      gp, H, hp_of(H), K, in_is_blstm, Hin, in_is_blstm ? hp_of(Hin) : 0, Kp, dir, g);
+  return ONSSEN_CHECK_LAUNCH();
+}

@@ -39,6 +39,15 @@ extern "C" int onssen_gemm_f16(const void* A, const void* W, const float* bias, 
                           (cudaStream_t)stream);
 }
 
+extern "C" int onssen_gemm_f16_ex(const void* A, const void* W, const float* bias, float* out, int M, int N,
+                                  int K, long long lda, long long ldw, long long ld_out, int epi, int group,
+                                  int remap_inner, int remap_outer, const float* out_scale, float* inv_norm,
+                                  void* stream) {
+  if (!A || !W || !out) return ONSSEN_ERR_ARG;
+  return onssen::gemm_f16(A, W, bias, out, M, N, K, lda, ldw, ld_out, epi, group, remap_inner, remap_outer,
+                          (cudaStream_t)stream, out_scale, inv_norm);
+}
+
 extern "C" int onssen_gemm_l2norm_supported(int group) { return onssen::gemm_l2norm_group_supported(group) ? 1 : 0; }
 
 extern "C" size_t onssen_bn_scratch_bytes(int M, int H) {

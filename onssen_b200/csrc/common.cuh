@@ -12,7 +12,7 @@ int num_sms();
 // internal C++ entry (defined in gemm_tc05.cu); the C ABI wrapper lives in capi.cu
 int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M, int N, int K, long long lda,
              long long ldw, long long ld_out, int epi, int group, int remap_inner, int remap_outer,
-             cudaStream_t stream);
+             cudaStream_t stream, const float* out_scale = nullptr, float* inv_norm = nullptr);
 bool gemm_l2norm_group_supported(int group);
 
 inline int hp_of(int H) { return ((H + 31) / 32) * 32; }

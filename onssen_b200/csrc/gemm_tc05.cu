@@ -41,6 +41,8 @@ struct GemmParams {
   int remap_outer;
   int block_n;
   int num_m_blocks, num_n_blocks;
+  const float* out_scale;  // optional device scalar: accumulators are multiplied by *out_scale (before bias)
+  float* inv_norm;         // optional (epi 3): 1/max(||z||,eps) per (output row, group) -> [rows][N/group]
 };
 
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
@@ -176,6 +178,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int i = lane; i < BN; i += 32)
         bias_s[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       __syncwarp();
+      const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.0f;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * MAX_BN;
@@ -205,10 +208,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float f[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-              f[j] = __uint_as_float(v[j]) + bias_s[g * D + j];
+              f[j] = fmaf(__uint_as_float(v[j]), oscale, bias_s[g * D + j]);
               ss = fmaf(f[j], f[j], ss);
             }
             const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            if (p.inv_norm != nullptr && m0 + lane < p.M)
+              p.inv_norm[out_row_off(m0 + lane) / p.ld_out * (p.N / D) + (nb / D)] = inv;
 #pragma unroll
             for (int j = 0; j < D; j += 4) {
               float4 o4 = make_float4(f[j] * inv, f[j + 1] * inv, f[j + 2] * inv, f[j + 3] * inv);
@@ -247,10 +252,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);   // smem broadcast
               float4 o4;
-              o4.x = act(__uint_as_float(v[j]) + b4.x);
-              o4.y = act(__uint_as_float(v[j + 1]) + b4.y);
-              o4.z = act(__uint_as_float(v[j + 2]) + b4.z);
-              o4.w = act(__uint_as_float(v[j + 3]) + b4.w);
+              o4.x = act(fmaf(__uint_as_float(v[j]), oscale, b4.x));
+              o4.y = act(fmaf(__uint_as_float(v[j + 1]), oscale, b4.y));
+              o4.z = act(fmaf(__uint_as_float(v[j + 2]), oscale, b4.z));
+              o4.w = act(fmaf(__uint_as_float(v[j + 3]), oscale, b4.w));
               *reinterpret_cast<float4*>(stg + lane * PITCH + j) = o4;
             }
           };
@@ -356,7 +361,7 @@ namespace onssen {
 // out: fp32. See GemmParams for epi/remap semantics.
 int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M, int N, int K, long long lda,
              long long ldw, long long ld_out, int epi, int group, int remap_inner, int remap_outer,
-             cudaStream_t stream) {
+             cudaStream_t stream, const float* out_scale, float* inv_norm) {
   if (M <= 0 || N <= 0 || K <= 0) return ONSSEN_ERR_ARG;
   if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return ONSSEN_ERR_ARG;
@@ -366,6 +371,7 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ld_out = ld_out; p.epi = epi; p.group = group;
   p.remap_inner = remap_inner; p.remap_outer = remap_outer; p.block_n = bn;
+  p.out_scale = out_scale; p.inv_norm = inv_norm;
   p.num_m_blocks = (M + BM - 1) / BM;
   p.num_n_blocks = (N + bn - 1) / bn;
   CUtensorMap ta, tw;

@@ -296,11 +296,18 @@ int launch_dc_fast(const float* emb, const void* label, const float* mag, int B,
   return ONSSEN_CHECK_LAUNCH();
 }
 
+// record layout of the partial / summed Gram records: "fast" = [D*D G][D*2 C][3 Y (y0y0,y0y1,y1y1)][msum],
+// generic = [D*D][D*S][S*S][msum]
+inline bool dc_fast_layout(const float* emb, int D, int S) {
+  if (S != 2 || (reinterpret_cast<uintptr_t>(emb) & 15) != 0) return false;
+  return D == 8 || D == 16 || D == 20 || D == 32 || D == 40 || D == 64;
+}
+
 template <typename LT>
 int dispatch_dc(const float* emb, const void* label, const float* mag, int B, int N, int D, int S,
                 float* scratch, cudaStream_t s, int* fast) {
   *fast = 1;
-  if (S == 2 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0) {
+  if (dc_fast_layout(emb, D, S)) {
     switch (D) {
       // 5x5 register tiles (measured on B200 at cfg2: 321 us; 10x10 tiles drop to 1 CTA/SM and take 636 us)
       case 20: return launch_dc_fast<20, 5, LT>(emb, label, mag, B, N, scratch, s);
@@ -317,6 +324,113 @@ int dispatch_dc(const float* emb, const void* label, const float* mag, int B, in
   const size_t smem = (size_t)(32 * D + 32 * S + 32) * 4;
   dim3 grid((N + DC_PTS_PER_CHUNK - 1) / DC_PTS_PER_CHUNK, B);
   loss_dc_partial_generic<LT><<<grid, DC_THREADS, smem, s>>>(emb, (const LT*)label, mag, N, D, S, scratch);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- loss_dc backward
+// d mean(...)/d e_n for utterance j (autograd of loss_dc.py:24-44):  with gl_j = sum_i g_bb[i][j] * msum_i,
+//   d e_n = gl_j / msum_j * ( 2 m_n s_n^2 (G e_n) / ||G||  -  2 m_n s_n (C y_n) / ||C|| ),
+// G = sum m s^2 e e^T (DxD), C = sum m s e y^T (Dx2) from the forward's summed record.  Thread d of a group
+// keeps row d of G in registers and streams points from a smem tile (float4 broadcast loads).
+template <int D, typename LT>
+__global__ void __launch_bounds__(256)
+loss_dc_bwd_kernel(const float* __restrict__ emb, const LT* __restrict__ label, const float* __restrict__ mag,
+                   const float* __restrict__ summed, int R, int msum_idx, const float* __restrict__ g_bb, int B,
+                   int N, float* __restrict__ d_emb) {
+  constexpr int GSZ = D <= 32 ? 32 : 64;
+  constexpr int NG = 256 / GSZ;
+  constexpr int P = 64;
+  __shared__ __align__(16) float e_s[P][D];
+  __shared__ float y_s[P][2];
+  __shared__ float m_s[P];
+  __shared__ double s_red[2][8];
+  __shared__ float s_coef[2];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int g = tid / GSZ;
+  const int d = tid % GSZ;
+  const float* rec = summed + (long long)b * R;
+  // norms of G and C (fp64 block reduction, same for every block of this utterance)
+  {
+    double q0 = 0.0, q1 = 0.0;
+    for (int i = tid; i < D * D; i += 256) q0 += (double)rec[i] * rec[i];
+    for (int i = tid; i < D * 2; i += 256) q1 += (double)rec[D * D + i] * rec[D * D + i];
+    q0 = warp_sum(q0); q1 = warp_sum(q1);
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = q0; s_red[1][tid >> 5] = q1; }
+    __syncthreads();
+    if (tid == 0) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int w = 0; w < 8; ++w) { t0 += s_red[0][w]; t1 += s_red[1][w]; }
+      const float msum = rec[msum_idx];
+      float gl = 0.f;
+      for (int i = 0; i < B; ++i) gl += g_bb[(long long)i * B + b] * summed[(long long)i * R + msum_idx];
+      const float ng = sqrtf((float)t0), nc = sqrtf((float)t1);
+      s_coef[0] = ng > 0.f ? gl * 2.0f / (msum * ng) : 0.f;
+      s_coef[1] = nc > 0.f ? gl * 2.0f / (msum * nc) : 0.f;
+    }
+    __syncthreads();
+  }
+  const float cg = s_coef[0], cc = s_coef[1];
+  float grow[D];
+  float c0 = 0.f, c1 = 0.f;
+  if (d < D) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) grow[k] = rec[d * D + k];
+    c0 = rec[D * D + d * 2];
+    c1 = rec[D * D + d * 2 + 1];
+  }
+  const int n_begin = blockIdx.x * DC_PTS_PER_CHUNK;
+  const int n_end = min(N, n_begin + DC_PTS_PER_CHUNK);
+  const float* eb = emb + (long long)b * N * D;
+  const LT* lb = label + (long long)b * N * 2;
+  const float* mb = mag + (long long)b * N;
+  float* ob = d_emb + (long long)b * N * D;
+  for (int n0 = n_begin; n0 < n_end; n0 += P) {
+    const int np = min(P, n_end - n0);
+    __syncthreads();
+    for (int i = tid; i < np; i += 256) {
+      y_s[i][0] = lab_to_f(lb[2 * (long long)(n0 + i)]);
+      y_s[i][1] = lab_to_f(lb[2 * (long long)(n0 + i) + 1]);
+      m_s[i] = mb[n0 + i];
+    }
+    for (int i = tid; i < np * D / 4; i += 256)
+      reinterpret_cast<float4*>(&e_s[0][0])[i] = reinterpret_cast<const float4*>(eb + (long long)n0 * D)[i];
+    __syncthreads();
+    if (d < D) {
+      for (int pnt = g; pnt < np; pnt += NG) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+          const float4 e4 = *reinterpret_cast<const float4*>(&e_s[pnt][k]);
+          acc = fmaf(grow[k], e4.x, acc);
+          acc = fmaf(grow[k + 1], e4.y, acc);
+          acc = fmaf(grow[k + 2], e4.z, acc);
+          acc = fmaf(grow[k + 3], e4.w, acc);
+        }
+        const float y0 = y_s[pnt][0], y1 = y_s[pnt][1];
+        const float sn = y0 + y1, m = m_s[pnt];
+        const float v = m * sn * (cg * sn * acc - cc * (c0 * y0 + c1 * y1));
+        ob[(long long)(n0 + pnt) * D + d] = v;
+      }
+    }
+  }
+}
+
+template <typename LT>
+int dispatch_dc_bwd(const float* emb, const void* label, const float* mag, const float* summed, int R, int msum_idx,
+                    const float* g_bb, int B, int N, int D, float* d_emb, cudaStream_t s) {
+  dim3 grid((N + DC_PTS_PER_CHUNK - 1) / DC_PTS_PER_CHUNK, B);
+#define ONSSEN_DC_BWD(DD)                                                                                  \
+  case DD:                                                                                                  \
+    loss_dc_bwd_kernel<DD, LT><<<grid, 256, 0, s>>>(emb, (const LT*)label, mag, summed, R, msum_idx, g_bb, B, N,  \
+                                                    d_emb);                                                    \
+    break;
+  switch (D) {
+    ONSSEN_DC_BWD(8) ONSSEN_DC_BWD(16) ONSSEN_DC_BWD(20) ONSSEN_DC_BWD(32) ONSSEN_DC_BWD(40) ONSSEN_DC_BWD(64)
+    ONSSEN_DC_BWD(4) ONSSEN_DC_BWD(12) ONSSEN_DC_BWD(24)
+    default: return ONSSEN_ERR_UNSUPPORTED;
+  }
+#undef ONSSEN_DC_BWD
   return ONSSEN_CHECK_LAUNCH();
 }
 
@@ -389,6 +503,25 @@ extern "C" int onssen_loss_dc_fwd(const float* emb, const void* label, int label
   loss_dc_final_kernel<<<B, 256, 0, s>>>(summed, 1, D, S, fast, l, mag_sum);
   if (loss_bb) loss_dc_outer_kernel<<<(B * B + 255) / 256, 256, 0, s>>>(l, mag_sum, B, loss_bb);
   return ONSSEN_CHECK_LAUNCH();
+}
+
+
+extern "C" int onssen_loss_dc_bwd(const float* emb, const void* label, int label_dtype, const float* mag,
+                                  const float* summed_record, const float* g_bb, int B, int N, int D, int S,
+                                  float* d_emb, void* stream) {
+  if (!emb || !label || !mag || !summed_record || !g_bb || !d_emb || B <= 0 || N <= 0) return ONSSEN_ERR_ARG;
+  // the fast forward layout (S == 2, D % 4 == 0) is the one the training path supports
+  if (S != 2 || (D & 3) || (reinterpret_cast<uintptr_t>(emb) & 15)) return ONSSEN_ERR_UNSUPPORTED;
+  const bool fast = dc_fast_layout(emb, D, S);
+  const int R = fast ? D * D + D * 2 + 4 : D * D + D * S + S * S + 1;
+  const int mi = R - 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (label_dtype) {
+    case ONSSEN_DT_F32: return dispatch_dc_bwd<float>(emb, label, mag, summed_record, R, mi, g_bb, B, N, D, d_emb, s);
+    case ONSSEN_DT_F64: return dispatch_dc_bwd<double>(emb, label, mag, summed_record, R, mi, g_bb, B, N, D, d_emb, s);
+    case ONSSEN_DT_U8: return dispatch_dc_bwd<uint8_t>(emb, label, mag, summed_record, R, mi, g_bb, B, N, D, d_emb, s);
+    default: return ONSSEN_ERR_ARG;
+  }
 }
 
 extern "C" int onssen_loss_pit_l1_fwd(const float* mask_a, const float* mask_b, long long mask_stride,

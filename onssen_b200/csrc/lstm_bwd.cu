@@ -1,0 +1,203 @@
+// BPTT for one BLSTM layer (autograd of torch.nn.LSTM as used at onssen/nn/deep_clustering.py:34-35; the
+// reference gets it from cuDNN through loss.backward(), onssen/utils/train.py:82).
+//
+// One launch per time step (both directions), no inter-CTA synchronisation inside a launch: CTA (unit block,
+// dir, batch block) owns 32 hidden units.  It first forms dh_rec[u][b] = sum_r W_hh[r][u] * dG_{prev}[r][b]
+// over ALL 4H gate rows of the previously processed step (mma.sync m16n8k16, fp16 operands, W_hh^T slice and
+// dG read from L2, K split over the 8 warps), then does the gate math for ITS units at this step and writes
+// dG (fp32, in place over the saved activations, and as scaled fp16 for the next launch / the wgrad GEMMs).
+// dh_rec and the cell-gradient carry never leave the CTA's unit block.  L2-bound: 2 x 4Hp x (32+B) fp16 per CTA.
+#include "common.cuh"
+
+namespace onssen {
+namespace {
+
+struct BwdParams {
+  float* actg;          // [T*B][2*4Hp] activated gates (i,f,g,o) -> overwritten with dG (fp32)
+  __half* dg16;         // [T*B][2*4Hp] scaled fp16 dG
+  const float* c;       // [T*B][2*Hp]
+  const float* dy;      // [T*B][2*Hp] gradient w.r.t. the layer output (after dropout)
+  const __half* wt;     // [2][Hp][4Hp] W_hh^T, permuted gate order
+  float* dc;            // [2][B][Hp] cell-gradient carry
+  const float* scale2;  // {scale, 1/scale}
+  int B, T, H, Hp, s;
+  float dropout_p;
+  unsigned int seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ float hash_uniform32(unsigned int seed_lo, unsigned int seed_hi, unsigned int idx) {
+  unsigned int x = idx ^ seed_lo;
+  x *= 0x9E3779B1u; x ^= x >> 15;
+  x *= 0x85EBCA77u; x ^= x >> 13;
+  x += seed_hi;
+  x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const BwdParams p) {
+  __shared__ float red[8][32][33];   // per-warp partial dh_rec[unit][batch]
+  const int Hp = p.Hp, B = p.B, T = p.T;
+  const int G4 = 4 * Hp;
+  const int ub = blockIdx.x, dir = blockIdx.y, bb = blockIdx.z;
+  const int b0 = bb * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int t = dir == 0 ? T - 1 - p.s : p.s;          // forward-time index handled by this launch
+  const int t_pp = dir == 0 ? t + 1 : t - 1;           // step processed by the previous launch
+  const int t_fp = dir == 0 ? t - 1 : t + 1;           // forward-time predecessor (c_{t-1} of this direction)
+  const float inv_scale = p.scale2[1], scale = p.scale2[0];
+
+  if (p.s > 0) {
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+    const __half* wt = p.wt + ((size_t)dir * Hp + ub * 32) * G4;
+    const __half* dg = p.dg16 + ((size_t)t_pp * B + b0) * (2 * G4) + (size_t)dir * G4;
+    const int ksteps = G4 / 16;
+    for (int ks = warp; ks < ksteps; ks += 8) {
+      const int k0 = ks * 16 + 2 * tq;
+      uint32_t a[2][4], bf[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const __half* r0 = wt + (size_t)(mt * 16 + g) * G4 + k0;
+        const __half* r1 = r0 + (size_t)8 * G4;
+        a[mt][0] = *reinterpret_cast<const uint32_t*>(r0);
+        a[mt][1] = *reinterpret_cast<const uint32_t*>(r1);
+        a[mt][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+        a[mt][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = nt * 8 + g;
+        if (b0 + n < B) {
+          const __half* r = dg + (size_t)n * (2 * G4) + k0;
+          bf[nt][0] = *reinterpret_cast<const uint32_t*>(r);
+          bf[nt][1] = *reinterpret_cast<const uint32_t*>(r + 8);
+        } else {
+          bf[nt][0] = bf[nt][1] = 0u;
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_16816(acc[mt][nt], a[mt], bf[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        red[warp][mt * 16 + g][nt * 8 + 2 * tq] = acc[mt][nt][0];
+        red[warp][mt * 16 + g][nt * 8 + 2 * tq + 1] = acc[mt][nt][1];
+        red[warp][mt * 16 + g + 8][nt * 8 + 2 * tq] = acc[mt][nt][2];
+        red[warp][mt * 16 + g + 8][nt * 8 + 2 * tq + 1] = acc[mt][nt][3];
+      }
+  }
+  __syncthreads();
+
+  const float keep_scale = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  for (int idx = tid; idx < 32 * 32; idx += 256) {
+    const int ul = idx & 31, bl = idx >> 5;
+    const int b = b0 + bl;
+    if (b >= B) continue;
+    const int u = ub * 32 + ul;
+    float dh_rec = 0.f;
+    if (p.s > 0) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) dh_rec += red[w][ul][bl];
+      dh_rec *= inv_scale;
+    }
+    const long long m = (long long)t * B + b;
+    const long long oy = m * (2 * Hp) + dir * Hp + u;
+    float dyv = p.dy[oy];
+    if (p.dropout_p > 0.f) {
+      const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)oy);
+      dyv = rnd < p.dropout_p ? 0.f : dyv * keep_scale;
+    }
+    const float dh = dyv + dh_rec;
+    float4* gp = reinterpret_cast<float4*>(p.actg + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul);
+    const float4 a4 = *gp;                              // i, f, g, o (activated)
+    const float ct = p.c[oy];
+    float cprev = 0.f;
+    if (t_fp >= 0 && t_fp < T) cprev = p.c[((long long)t_fp * B + b) * (2 * Hp) + dir * Hp + u];
+    const float tc = tanhf(ct);
+    float* dcp = p.dc + ((size_t)dir * B + b) * Hp + u;
+    const float dct = dh * a4.w * (1.0f - tc * tc) + (p.s > 0 ? *dcp : 0.f);
+    float4 d4;
+    d4.x = dct * a4.z * a4.x * (1.0f - a4.x);          // di (pre-activation)
+    d4.y = dct * cprev * a4.y * (1.0f - a4.y);         // df
+    d4.z = dct * a4.x * (1.0f - a4.z * a4.z);          // dg
+    d4.w = dh * tc * a4.w * (1.0f - a4.w);             // do
+    *dcp = dct * a4.y;
+    *gp = d4;
+    __half2 lo = __halves2half2(to_half_sat(d4.x * scale), to_half_sat(d4.y * scale));
+    __half2 hi = __halves2half2(to_half_sat(d4.z * scale), to_half_sat(d4.w * scale));
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p.dg16 + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul) = o;
+  }
+}
+
+// W_hh [4H][H] fp32 (both directions) -> wt [2][Hp units][4Hp permuted gate rows] fp16
+__global__ void pack_whh_t_kernel(const float* __restrict__ w_f, const float* __restrict__ w_r, int H, int Hp,
+                                  __half* __restrict__ out) {
+  const long long total = 2LL * Hp * 4 * Hp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % (4 * Hp));
+    long long tt = idx / (4 * Hp);
+    const int u = (int)(tt % Hp);
+    const int dir = (int)(tt / Hp);
+    const int rb = r >> 7, ul = (r & 127) >> 2, gate = r & 3;
+    const int ur = rb * 32 + ul;
+    float v = 0.f;
+    if (ur < H && u < H) v = (dir ? w_r : w_f)[(long long)(gate * H + ur) * H + u];
+    out[idx] = to_half_sat(v);
+  }
+}
+
+}  // namespace
+}  // namespace onssen
+
+using namespace onssen;
+
+extern "C" int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, int H, void* out, void* stream) {
+  if (!w_hh_f || !w_hh_r || !out || H <= 0) return ONSSEN_ERR_ARG;
+  const int Hp = hp_of(H);
+  long long g = (2LL * Hp * 4 * Hp + 255) / 256;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  pack_whh_t_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w_hh_f, w_hh_r, H, Hp, (__half*)out);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
+                                    float* dc_carry, const float* scale2, int B, int T, int H, float dropout_p,
+                                    unsigned long long seed, unsigned long long offset, void* stream) {
+  if (!act_gates || !dg16 || !c || !dy || !whh_t || !dc_carry || !scale2 || B <= 0 || T <= 0 || H <= 0)
+    return ONSSEN_ERR_ARG;
+  BwdParams p;
+  p.actg = act_gates; p.dg16 = (__half*)dg16; p.c = c; p.dy = dy; p.wt = (const __half*)whh_t; p.dc = dc_carry;
+  p.scale2 = scale2; p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H);
+  p.dropout_p = dropout_p;
+  const unsigned long long mix = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
+  p.seed_lo = (unsigned int)mix;
+  p.seed_hi = (unsigned int)(mix >> 32);
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(p.Hp / 32, 2, (B + 31) / 32);
+  for (int step = 0; step < T; ++step) {
+    p.s = step;
+    lstm_bwd_step_kernel<<<grid, 256, 0, s>>>(p);
+  }
+  return ONSSEN_CHECK_LAUNCH();
+}

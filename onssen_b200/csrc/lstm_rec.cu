@@ -49,6 +49,10 @@ struct RecParams {
   float dropout_p;
   unsigned int seed_lo, seed_hi;
   long long* trace;  // debug: clock64 stamps of CTA 0, steps [TRACE_S0, TRACE_S0+4)
+  // training: state saved for BPTT (all optional)
+  float* act_out;    // == gates: activated i,f,g,o written in place over the consumed pre-activations
+  float* c_out;      // [T*B][2*Hp] cell state
+  __half* h_raw;     // [T*B][2*Hp] h before dropout (operand of the W_hh weight gradient)
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -328,7 +332,11 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
 #pragma unroll
       for (int j = 0; j < NBH; ++j) {
         const float pre = acc[j] + gpre[j];
-        xch[r * XP + jbase + j] = fmaf(ak, sigmoid_f(ak * pre), ab);
+        const float av = fmaf(ak, sigmoid_f(ak * pre), ab);
+        xch[r * XP + jbase + j] = av;
+        // in place: this element was consumed (prefetched) two steps ago
+        if (p.act_out != nullptr && jbase + j < nb_valid)
+          p.act_out[((long long)t * p.B + b0 + jbase + j) * ldg + (long long)dir * 4 * Hp + rb * 128 + r] = av;
       }
       __syncwarp();
       if (tid == 0) REC_TRACE(10);
@@ -373,6 +381,8 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
           }
           if (p.y_h) p.y_h[o] = __float2half_rn(hv);
           if (p.y_f) p.y_f[o] = hv;
+          if (p.c_out) p.c_out[o] = c_state[ci];
+          if (p.h_raw) p.h_raw[o] = __float2half_rn(hval[ci]);
         }
       }
       {
@@ -505,10 +515,32 @@ extern "C" size_t onssen_blstm_rec_workspace_bytes(int B, int H) {
   return 256 + (size_t)2 * 2 * smax * Hp * 32 * 2;
 }
 
+static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
+                        float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
+                        size_t workspace_bytes, int use_tensor_cores, void* stream, float* act_out, float* c_out,
+                        void* h_raw);
+
 extern "C" int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B, int T, int H, void* y_h,
                                     float* y_f, float dropout_p, unsigned long long seed,
                                     unsigned long long offset, void* workspace, size_t workspace_bytes,
                                     int use_tensor_cores, void* stream) {
+  return rec_fwd_impl(gates, whh_p, B, T, H, y_h, y_f, dropout_p, seed, offset, workspace, workspace_bytes,
+                      use_tensor_cores, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int T, int H, void* y_h,
+                                          float* y_f, float* c_out, void* h_raw, float dropout_p,
+                                          unsigned long long seed, unsigned long long offset, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (!c_out) return ONSSEN_ERR_ARG;
+  return rec_fwd_impl(gates_inout, whh_p, B, T, H, y_h, y_f, dropout_p, seed, offset, workspace, workspace_bytes, 1,
+                      stream, gates_inout, c_out, h_raw);
+}
+
+static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
+                        float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
+                        size_t workspace_bytes, int use_tensor_cores, void* stream, float* act_out, float* c_out,
+                        void* h_raw) {
   if (!gates || !whh_p || !workspace || B <= 0 || T <= 0 || H <= 0) return ONSSEN_ERR_ARG;
   if (!y_h && !y_f) return ONSSEN_ERR_ARG;
   if (dropout_p < 0.f || dropout_p >= 1.f) return ONSSEN_ERR_ARG;
@@ -525,6 +557,7 @@ extern "C" int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B
   p.seed_lo = (unsigned int)mix;
   p.seed_hi = (unsigned int)(mix >> 32);
   p.trace = g_trace_ptr;
+  p.act_out = act_out; p.c_out = c_out; p.h_raw = (__half*)h_raw;
   const size_t hbuf_bytes = (size_t)2 * 2 * sp.S * p.Hp * sp.NBP * 2;
   if (workspace_bytes < 256 + hbuf_bytes) return ONSSEN_ERR_ARG;
   p.flags = (unsigned int*)workspace;

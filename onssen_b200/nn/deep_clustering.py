@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward, require_no_grad
+from ._blstm import PackCache, blstm_forward
 
 
 class deep_clustering(nn.Module):
@@ -25,7 +25,12 @@ class deep_clustering(nn.Module):
     def forward(self, input):
         assert len(input) == 1, "There must be one tensor in the input for the deep clustering model"
         x = input[0].float()
-        require_no_grad("deep_clustering", x, self.fc_dc.weight)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if not self.training:
+                raise NotImplementedError("deep_clustering: gradients are implemented for train() mode "
+                                          "(batch-statistics BatchNorm), call model.train()")
+            from ._train import DCFunction
+            return [DCFunction.apply(self, x, *[p for _, p in self.named_parameters()])]
         B, T, F = x.shape
         H, D = self.hidden_dim, self.embedding_dim
         M = T * B

@@ -79,6 +79,16 @@ def main():
             emb_train, = dc([tt(feat)])
             loss_train = onssen.loss.loss_dc([emb_train], [tt(oh), tt(mix)])
             sd_after = sd_to_np(dc.state_dict())
+        # gradients of torch.mean(loss_dc) in train mode (train.py:77-82) w.r.t. every parameter and the embedding
+        dc.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=False)
+        dc.train()
+        dc.zero_grad()
+        emb_g, = dc([tt(feat)])
+        emb_g.retain_grad()
+        torch.mean(onssen.loss.loss_dc([emb_g], [tt(oh), tt(mix)])).backward()
+        grads = {"g:" + k: v.grad.detach().numpy().copy() for k, v in dc.named_parameters()}
+        grads["g:embedding"] = emb_g.grad.detach().numpy().copy()
+        np.savez_compressed(os.path.join(out_dir, f"dcgrad_{name}.npz"), **grads)
         np.savez_compressed(os.path.join(out_dir, f"dc_{name}.npz"), cfg=np.array([B, T, F, H, L, D]), feature=feat,
                             one_hot=oh, mag_mix=mix, emb_eval=emb_eval.numpy(), loss_eval=loss_eval.numpy(),
                             emb_train=emb_train.numpy(), loss_train=loss_train.numpy(),

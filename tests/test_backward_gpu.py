@@ -1,0 +1,70 @@
+"""Training path: gradients of torch.mean(loss_dc(model(x))) from the hand-written backward vs the gradients
+the REFERENCE's autograd produced (golden fixtures tests/golden/dcgrad_*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_loss_dc_backward_vs_reference(cuda_device):
+    import onssen_b200 as ob
+    for name in ("small", "mid"):
+        _, g = load_golden(f"dc_{name}.npz")
+        gz = np.load(f"tests/golden/dcgrad_{name}.npz")
+        emb = torch.from_numpy(g["emb_train"]).to(cuda_device).requires_grad_(True)
+        loss = ob.loss.loss_dc([emb], [torch.from_numpy(g["one_hot"]).to(cuda_device),
+                                       torch.from_numpy(g["mag_mix"]).to(cuda_device)])
+        torch.mean(loss).backward()
+        # the fixture's gradient was taken at the reference's own train-mode embedding
+        assert rel_err(emb.grad.cpu().numpy(), gz["g:embedding"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_deep_clustering_gradients_vs_reference(cuda_device, name):
+    import onssen_b200 as ob
+    p, g = load_golden(f"dc_{name}.npz")
+    gz = np.load(f"tests/golden/dcgrad_{name}.npz")
+    B, T, F, H, L, D = [int(v) for v in g["cfg"]]
+    model = ob.nn.deep_clustering(F, H, L, D, dropout=0.0).to(cuda_device).train()
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()}, strict=False)
+    cu = lambda a: torch.from_numpy(a).to(cuda_device)
+    emb, = model([cu(g["feature"])])
+    assert emb.requires_grad
+    torch.mean(ob.loss.loss_dc([emb], [cu(g["one_hot"]), cu(g["mag_mix"])])).backward()
+    worst = 0.0
+    for k, v in model.named_parameters():
+        assert v.grad is not None, k
+        e = rel_err(v.grad.cpu().numpy(), gz["g:" + k])
+        worst = max(worst, e)
+        print(f"{k:28s} rel err {e:.3e}  |g|={np.linalg.norm(gz['g:' + k]):.3e}")
+        assert e < 3e-2, (k, e)
+    print("worst relative gradient error", worst)
+
+
+def test_training_step_reduces_loss(cuda_device):
+    """trainer-style optimisation steps on one synthetic batch: the loss must go down."""
+    import onssen_b200 as ob
+    from oracle import onssen_oracle as O
+    torch.manual_seed(0)
+    B, T = 4, 60
+    model = ob.nn.deep_clustering(129, 64, 2, 20, dropout=0.3).to(cuda_device).train()
+    utts = [O.synth_utterance(i, 8000) for i in range(B)]
+    cu = lambda k: torch.from_numpy(np.stack([u[k] for u in utts])).to(cuda_device)
+    inp, lab = ob.data.featurize_batch(cu(0), cu(1), cu(2), "dc", 256, 64, T, 40, crop_start=torch.zeros(B, dtype=torch.int32))
+    opt = ob.utils.build_optimizer(model.parameters(), {"name": "adam", "lr": 1e-3})
+    losses = []
+    for _ in range(12):
+        loss = torch.mean(ob.loss.loss_dc(model(inp), lab))
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+        opt.step()
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and losses[-1] < 0.9 * losses[0], losses
