@@ -213,9 +213,42 @@ def run_gpu(args):
         f1.record()
         barrier()
         ms_e2e = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    # ---------------- training step (secondary figure): fwd + loss + backward (+ grad all-reduce) + clip + Adam
+    ms_train = None
+    if not args.no_train:
+        from onssen_b200.utils.ddp import GradSync, broadcast_parameters
+        if world > 1:
+            broadcast_parameters(model)
+            model.grad_sync = GradSync()
+        opt = ob.utils.build_optimizer(model.parameters(), {"name": "adam", "lr": 1e-3})
+
+        def train_step(ws, st):
+            inp, lab = ob.data.featurize_batch(ws[0], ws[1], ws[2], "dc", CFG["n_fft"], CFG["hop"], T, CFG["db"],
+                                               crop_start=st)
+            loss = torch.mean(ob.loss.loss_dc(model(inp), lab))
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+            opt.step()
+            return loss
+
+        KT = max(3, K // 4)
+        for i in range(2):
+            train_step(*dev_batches[i % nbatch])
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(KT):
+            tl = train_step(*dev_batches[i % nbatch])
+        g1.record()
+        barrier()
+        ms_train = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        train_loss = float(tl.item())
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+        if ms_train is not None:
+            dist.all_reduce(ms_train, op=dist.ReduceOp.MAX)
     if rank == 0:
         pk, pk_src = peaks()
         total = ms.item() / 1e3
@@ -257,6 +290,11 @@ def run_gpu(args):
                                  "sample": f"{sample} utterances x 2 steps, numpy oracle port (featurizer+fwd+loss), "
                                            f"{cpu_step:.2f} s/step"},
                 "loss_mean_last": lv}
+        if ms_train is not None:
+            line["train"] = {"value": world * B * KT / (ms_train.item() / 1e3), "unit": "utterances/s",
+                             "ms_per_step": ms_train.item() / KT, "steps": KT, "loss_last": train_loss,
+                             "includes": "featurizer + forward + loss_dc + hand-written backward (BPTT) + "
+                                         "bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm_(5) + Adam"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -268,6 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step figure")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -48,7 +48,9 @@ def dc_forward_train(model, x):
     return emb, saved
 
 
-def dc_backward(model, saved, d_emb):
+def dc_backward(model, saved, d_emb, on_grads=None):
+    """on_grads(dict) is called with each group of gradients as soon as it is final (head+BN, then every BLSTM
+    layer from the top): the hook point for the overlapped data-parallel all-reduce (utils/ddp.py)."""
     rnn, bn = model.rnn, model.bn
     B, T, F = saved["shape"]
     H, L, D = rnn.hidden_size, rnn.num_layers, model.embedding_dim
@@ -73,8 +75,11 @@ def dc_backward(model, saved, d_emb):
     # ---- BatchNorm1d
     dY, grads["bn.weight"], grads["bn.bias"] = _lib.bn_backward(dA, saved["y_f"], M, H, bn.weight.detach(),
                                                                 saved["mean"], saved["invstd"])
+    if on_grads is not None:
+        on_grads(dict(grads))
     # ---- BLSTM, top layer first
     for l in reversed(range(L)):
+        done_before = set(grads)
         lay = saved["layers"][l]
         wih_p, _, _ = saved["packed"][l]
         (wf, wr) = lstm_layer_params(rnn, l)
@@ -106,6 +111,9 @@ def dc_backward(model, saved, d_emb):
             _lib.gemm_f16_ex(dg16, wihT, None, dX, M, kp_in, 8 * Hp, kp_in, out_scale=inv)
             dY = dX
         lay["gates"] = None
+        if on_grads is not None:
+            # bias_ih / bias_hh share one tensor: reduce it once
+            on_grads({k: v for k, v in grads.items() if k not in done_before and "bias_hh" not in k})
     return grads
 
 
@@ -121,6 +129,9 @@ class DCFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_emb):
-        grads = dc_backward(ctx.model, ctx.saved, d_emb.contiguous())
+        sync = getattr(ctx.model, "grad_sync", None)
+        grads = dc_backward(ctx.model, ctx.saved, d_emb.contiguous(), None if sync is None else sync.reduce_bucket)
+        if sync is not None:
+            sync.wait()
         ctx.saved = None
         return (None, None) + tuple(grads[n] for n in ctx.names)

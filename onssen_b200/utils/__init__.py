@@ -2,6 +2,6 @@
 from .basic import AttrDict, AverageMeter, build_optimizer
 from .test import tester, tester_chimera, tester_dc
 from .train import trainer
-from . import dist
+from . import ddp, dist
 
-__all__ = ["AttrDict", "AverageMeter", "build_optimizer", "trainer", "tester", "tester_dc", "tester_chimera", "dist"]
+__all__ = ["AttrDict", "AverageMeter", "build_optimizer", "trainer", "tester", "tester_dc", "tester_chimera", "dist", "ddp"]

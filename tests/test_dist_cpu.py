@@ -41,6 +41,24 @@ def _worker(rank, world, port, ret):
     assert abs(got - want) < 1e-9 * abs(want) + 1e-9, (got, want)
     # and it differs from the naive mean of per-shard means (why the 4-scalar reduction exists)
     naive = D.sum_over_ranks(float((l_all[lo:hi][None, :] * m_all[lo:hi][:, None]).double().mean())) / world
+    # bucketed gradient all-reduce (gloo here, NCCL on the GPU box): rank average, shared bias tensor reduced once
+    from onssen_b200.utils.ddp import GradSync, broadcast_parameters
+    sync = GradSync()
+    gb = torch.full((5,), float(rank + 1))
+    g1 = {"fc.weight": torch.full((3, 4), float(rank + 1)), "fc.bias": torch.arange(4.0) * (rank + 1)}
+    g2 = {"rnn.weight_ih_l0": torch.ones(6, 2) * (10 * (rank + 1)), "rnn.bias_ih_l0": gb}
+    sync.reduce_bucket(g1)
+    sync.reduce_bucket(g2)
+    sync.wait()
+    avg = sum(range(1, world + 1)) / world
+    assert torch.allclose(g1["fc.weight"], torch.full((3, 4), avg)) and torch.allclose(g1["fc.bias"], torch.arange(4.0) * avg)
+    assert torch.allclose(g2["rnn.weight_ih_l0"], torch.ones(6, 2) * 10 * avg) and torch.allclose(gb, torch.full((5,), avg))
+    assert sync.bytes_reduced == (12 + 4 + 12 + 5) * 4
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(float(rank))
+    broadcast_parameters(lin, 0)
+    assert float(lin.weight.abs().max()) == 0.0
     ret[rank] = (got, naive, want)
     dist.barrier()
     dist.destroy_process_group()
