@@ -226,7 +226,9 @@ int onssen_bn_backward(const float* d_out, const float* y, int M, int H, const f
 int onssen_unpack_linear_grad(const float* gp, int N, int K, int in_is_blstm, int Hin, int Kp, float* g, void* stream);
 int onssen_unpack_lstm_grad(const float* gp, int H, int K, int in_is_blstm, int Hin, int Kp, int dir, float* g,
                             void* stream);
-/* W_hh (both directions, fp32 [4H][H]) -> fp16 [2][Hp][4Hp]: transposed, permuted gate rows, zero padded. */
+/* W_hh (both directions, fp32 [4H][H]) -> fp16, 2*Hp*4Hp elements: W_hh^T pre-laid-out in mma.m16n8k16 A-fragment
+ * order [dir][unit block][k-step][m-tile][lane][4 words] (permuted gate rows, zero padded) so that every operand
+ * load of the BPTT step kernel is one coalesced 16-byte access. */
 int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, int H, void* out, void* stream);
 /* Forward recurrence that also saves the BPTT state: the activated gates overwrite gates_inout in place, c_out
  * [T*B][2Hp] fp32, h_raw [T*B][2Hp] fp16 = h before dropout (NULL when dropout_p == 0: use y_h). */
@@ -235,9 +237,11 @@ int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int
                                unsigned long long offset, void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT over one layer, both directions (one launch per step). act_gates: saved activations, overwritten with the
  * fp32 pre-activation gradients dG; dg16 receives dG * scale2[0] in fp16; dy = gradient w.r.t. the layer output
- * (the dropout mask is re-derived from seed/offset); dc_carry [2][B][Hp] scratch. */
+ * (the dropout mask is re-derived from seed/offset); scratch: onssen_blstm_rec_bwd_scratch_bytes(B, H) (cell
+ * gradient carry + the per-step dG exchange buffer in B-fragment order), zeroed by the call. */
+size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H);
 int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
-                         float* dc_carry, const float* scale2, int B, int T, int H, float dropout_p,
+                         void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
                          unsigned long long seed, unsigned long long offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

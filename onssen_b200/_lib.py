@@ -61,6 +61,7 @@ _SIGNATURES = {
     "onssen_lstm_pack_whh_t": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "onssen_blstm_rec_fwd_train": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_ull, c_ull,
                                            c_vp, c_sz, c_vp]),
+    "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
     "onssen_mul_pack_f16": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_int, c_vp]),
     "onssen_pack_phase_input_f16": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
@@ -534,7 +535,7 @@ def blstm_rec_fwd_train(gates, whh_p, B, T, H, y_h, y_f, c_out, h_raw, dropout_p
 
 def blstm_rec_bwd(act_gates, dg16, c, dy, whh_t, scale2, B, T, H, dropout_p, seed, offset):
     lib = load()
-    dc = torch.zeros(2, B, hp_of(H), device=c.device, dtype=torch.float32)
-    rc = lib.onssen_blstm_rec_bwd(_p(act_gates), _p(dg16), _p(c), _p(_req(dy, torch.float32)), _p(whh_t), _p(dc),
+    scratch = torch.empty(lib.onssen_blstm_rec_bwd_scratch_bytes(B, H), device=c.device, dtype=torch.uint8)
+    rc = lib.onssen_blstm_rec_bwd(_p(act_gates), _p(dg16), _p(c), _p(_req(dy, torch.float32)), _p(whh_t), _p(scratch),
                                   _p(scale2), B, T, H, float(dropout_p), int(seed), int(offset), _stream())
     _check(rc, "onssen_blstm_rec_bwd")

@@ -17,7 +17,8 @@ struct BwdParams {
   __half* dg16;         // [T*B][2*4Hp] scaled fp16 dG
   const float* c;       // [T*B][2*Hp]
   const float* dy;      // [T*B][2*Hp] gradient w.r.t. the layer output (after dropout)
-  const __half* wt;     // [2][Hp][4Hp] W_hh^T, permuted gate order
+  const uint32_t* wt;   // W_hh^T in mma A-fragment order: [dir][ub][kstep][mtile][lane][4 words]
+  uint32_t* frag;       // dG of the last processed step in B-fragment order: [parity][dir][bb][kstep][ntile][lane][2]
   float* dc;            // [2][B][Hp] cell-gradient carry
   const float* scale2;  // {scale, 1/scale}
   int B, T, H, Hp, s;
@@ -62,36 +63,39 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const BwdParams p) {
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-    const __half* wt = p.wt + ((size_t)dir * Hp + ub * 32) * G4;
-    const __half* dg = p.dg16 + ((size_t)t_pp * B + b0) * (2 * G4) + (size_t)dir * G4;
     const int ksteps = G4 / 16;
-    for (int ks = warp; ks < ksteps; ks += 8) {
-      const int k0 = ks * 16 + 2 * tq;
-      uint32_t a[2][4], bf[4][2];
+    const int nub = Hp / 32, nbb = gridDim.z;
+    const uint4* wfr = reinterpret_cast<const uint4*>(p.wt) + ((size_t)(dir * nub + ub) * ksteps) * 2 * 32 + lane;
+    const uint2* bfr = reinterpret_cast<const uint2*>(p.frag) +
+                       ((((size_t)((p.s - 1) & 1) * 2 + dir) * nbb + bb) * ksteps) * 4 * 32 + lane;
+    // each warp owns a contiguous range of k-steps; operands are pre-laid-out in fragment order, so every load is
+    // one fully coalesced 16-byte (A) / 8-byte (B) access; U k-steps of loads are issued before their MMAs
+    const int per_warp = (ksteps + 7) / 8;
+    const int ks_begin = warp * per_warp;
+    const int ks_end = min(ksteps, ks_begin + per_warp);
+    constexpr int U = 4;    // measured: U=10 makes ptxas serialise the loads again (64 regs) and is slower
+    for (int ksb = ks_begin; ksb < ks_end; ksb += U) {
+      uint4 a[U][2];
+      uint2 bf[U][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const __half* r0 = wt + (size_t)(mt * 16 + g) * G4 + k0;
-        const __half* r1 = r0 + (size_t)8 * G4;
-        a[mt][0] = *reinterpret_cast<const uint32_t*>(r0);
-        a[mt][1] = *reinterpret_cast<const uint32_t*>(r1);
-        a[mt][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
-        a[mt][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+      for (int uu = 0; uu < U; ++uu) {
+        const int ks = min(ksb + uu, ks_end - 1);          // clamped: duplicates are skipped below
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) a[uu][mt] = __ldg(wfr + ((size_t)ks * 2 + mt) * 32);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[uu][nt] = bfr[((size_t)ks * 4 + nt) * 32];
       }
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int n = nt * 8 + g;
-        if (b0 + n < B) {
-          const __half* r = dg + (size_t)n * (2 * G4) + k0;
-          bf[nt][0] = *reinterpret_cast<const uint32_t*>(r);
-          bf[nt][1] = *reinterpret_cast<const uint32_t*>(r + 8);
-        } else {
-          bf[nt][0] = bf[nt][1] = 0u;
+      for (int uu = 0; uu < U; ++uu) {
+        if (ksb + uu < ks_end) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              mma_16816(acc[mt][nt], reinterpret_cast<const uint32_t*>(&a[uu][mt]),
+                        reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
         }
       }
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_16816(acc[mt][nt], a[mt], bf[nt]);
     }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -146,19 +150,39 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const BwdParams p) {
     o.x = *reinterpret_cast<uint32_t*>(&lo);
     o.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(p.dg16 + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul) = o;
+    // the same values in the next launch's B-fragment order: row r = ub*128 + 4*ul + gate is k-index
+    // kk = (4*ul + gate) % 16 of k-step ub*8 + ul/4; words pair (kk, kk+1); column n = bl
+    {
+      const int ks = ub * 8 + (ul >> 2);
+      const int j = ul & 3;                       // kk = 4*j + gate
+      const int reg = j >> 1;                     // kk >= 8 -> second B register
+      const int tq0 = (j & 1) * 2;                // (kk % 8) / 2 for gate pair (0,1); +1 for gates (2,3)
+      uint32_t* fb = p.frag + (((((size_t)(p.s & 1) * 2 + dir) * gridDim.z + bb) * (G4 / 16) + ks) * 4 + (bl >> 3)) * 64;
+      fb[((bl & 7) * 4 + tq0) * 2 + reg] = o.x;
+      fb[((bl & 7) * 4 + tq0 + 1) * 2 + reg] = o.y;
+    }
   }
 }
 
-// W_hh [4H][H] fp32 (both directions) -> wt [2][Hp units][4Hp permuted gate rows] fp16
+// W_hh [4H][H] fp32 (both directions) -> W_hh^T in mma.m16n8k16 A-fragment order (fp16):
+// [dir][ub][kstep][mtile][lane][word w][2 halves];  word w covers row = mtile*16 + lane/4 + 8*(w&1) (hidden unit
+// ub*32 + row) and k = 16*kstep + 2*(lane%4) + 8*(w>>1) + {0,1} (permuted gate row index)
 __global__ void pack_whh_t_kernel(const float* __restrict__ w_f, const float* __restrict__ w_r, int H, int Hp,
                                   __half* __restrict__ out) {
-  const long long total = 2LL * Hp * 4 * Hp;
+  const int nub = Hp / 32, ksteps = 4 * Hp / 16;
+  const long long total = 2LL * nub * ksteps * 2 * 32 * 4 * 2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(idx % (4 * Hp));
-    long long tt = idx / (4 * Hp);
-    const int u = (int)(tt % Hp);
-    const int dir = (int)(tt / Hp);
+    long long tt = idx;
+    const int e = (int)(tt & 1); tt >>= 1;
+    const int w = (int)(tt & 3); tt >>= 2;
+    const int lane = (int)(tt & 31); tt >>= 5;
+    const int mt = (int)(tt & 1); tt >>= 1;
+    const int ks = (int)(tt % ksteps); tt /= ksteps;
+    const int ub = (int)(tt % nub);
+    const int dir = (int)(tt / nub);
+    const int u = ub * 32 + mt * 16 + (lane >> 2) + 8 * (w & 1);
+    const int r = 16 * ks + 2 * (lane & 3) + 8 * (w >> 1) + e;
     const int rb = r >> 7, ul = (r & 127) >> 2, gate = r & 3;
     const int ur = rb * 32 + ul;
     float v = 0.f;
@@ -181,19 +205,28 @@ extern "C" int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, 
   return ONSSEN_CHECK_LAUNCH();
 }
 
+extern "C" size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H) {
+  const int Hp = hp_of(H);
+  // dc carry [2][B][Hp] fp32 + fragment exchange [2 parity][2 dir][nbb][4Hp/16][4][32][2] u32
+  return (size_t)2 * B * Hp * 4 + (size_t)2 * 2 * ((B + 31) / 32) * (4 * Hp / 16) * 4 * 32 * 2 * 4;
+}
+
 extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
-                                    float* dc_carry, const float* scale2, int B, int T, int H, float dropout_p,
+                                    void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
                                     unsigned long long seed, unsigned long long offset, void* stream) {
-  if (!act_gates || !dg16 || !c || !dy || !whh_t || !dc_carry || !scale2 || B <= 0 || T <= 0 || H <= 0)
+  if (!act_gates || !dg16 || !c || !dy || !whh_t || !scratch || !scale2 || B <= 0 || T <= 0 || H <= 0)
     return ONSSEN_ERR_ARG;
+  float* dc_carry = (float*)scratch;
   BwdParams p;
-  p.actg = act_gates; p.dg16 = (__half*)dg16; p.c = c; p.dy = dy; p.wt = (const __half*)whh_t; p.dc = dc_carry;
+  p.actg = act_gates; p.dg16 = (__half*)dg16; p.c = c; p.dy = dy; p.wt = (const uint32_t*)whh_t; p.dc = dc_carry;
+  p.frag = (uint32_t*)((uint8_t*)scratch + (size_t)2 * B * hp_of(H) * 4);
   p.scale2 = scale2; p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H);
   p.dropout_p = dropout_p;
   const unsigned long long mix = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
   p.seed_lo = (unsigned int)mix;
   p.seed_hi = (unsigned int)(mix >> 32);
   cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(scratch, 0, onssen_blstm_rec_bwd_scratch_bytes(B, H), s) != cudaSuccess) return ONSSEN_ERR_CUDA;
   dim3 grid(p.Hp / 32, 2, (B + 31) / 32);
   for (int step = 0; step < T; ++step) {
     p.s = step;
