@@ -140,6 +140,8 @@ int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B, int T, in
 /* Debug/profiling hook: when set to a device buffer of 64 int64, the next recurrent launches record clock64
  * stamps of CTA 0 for steps 100..103 (16 slots per step; see REC_TRACE in csrc/lstm_rec.cu). NULL disables. */
 void onssen_blstm_rec_set_trace(void* device_buf_64_int64);
+/* Tuning knob: SM cycles every CTA waits between publishing h_t and its first gather round (default tuned on B200). */
+void onssen_blstm_rec_set_poll_delay(int cycles);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm1d over (B,T) per channel (replaces permute + nn.BatchNorm1d + permute,

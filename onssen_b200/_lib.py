@@ -34,6 +34,7 @@ _SIGNATURES = {
     "onssen_gemm_f16": (c_int, [c_vp] * 4 + [c_int] * 3 + [c_ll] * 3 + [c_int] * 4 + [c_vp]),
     "onssen_blstm_rec_workspace_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_set_trace": (None, [c_vp]),
+    "onssen_blstm_rec_set_poll_delay": (None, [c_int]),
     "onssen_blstm_rec_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_f, c_ull, c_ull, c_vp, c_sz,
                                      c_int, c_vp]),
     "onssen_bn_num_chunks": (c_int, [c_int]),

@@ -37,6 +37,7 @@ constexpr int NACC = 4;   // independent accumulators (columns a*NBP): back-to-b
                           // serialise on the ~70-cycle accumulate latency when N is this small
 constexpr int TRACE_S0 = 100;
 long long* g_trace_ptr = nullptr;
+int g_poll_delay = 0;   // SM cycles to wait between publishing h_t and the first gather round (tuning knob)
 
 struct RecParams {
   const float* gates;
@@ -50,6 +51,7 @@ struct RecParams {
   unsigned int seed_lo, seed_hi;
   long long* trace;  // debug: clock64 stamps of CTA 0, steps [TRACE_S0, TRACE_S0+4)
   // training: state saved for BPTT (all optional)
+  int poll_delay;
   float* act_out;    // == gates: activated i,f,g,o written in place over the consumed pre-activations
   float* c_out;      // [T*B][2*Hp] cell state
   __half* h_raw;     // [T*B][2*Hp] h before dropout (operand of the W_hh weight gradient)
@@ -95,8 +97,9 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* v) {
 // as a per-element step-parity flag.  A buffer (selected by s&1) is rewritten every 2 steps with the flag bit
 // toggled, so a reader knows an element is fresh from the element itself: no fences, no counters, no extra
 // bytes (the NCCL "LL" idea at 1 bit per element).  Stores are 4-byte relaxed (two units of one column).
-__device__ __forceinline__ void st_relaxed_u32(void* p, unsigned int v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_v4(void* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
 }
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
   uint4 v;
@@ -357,13 +360,19 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
         c_state[ci] = c;
         const float h = go * fmaf(2.0f, sigmoid_f(2.0f * c), -1.0f);
         hval[ci] = h;
-        // publish: units (u, u+1) of column j share one 4-byte word; lane+4 holds unit u+1
-        const float hn = __shfl_down_sync(0xffffffffu, h, 4);
-        if ((ul & 1) == 0) {
-          const __half2 pk = __floats2half2_rn(h, hn);
-          st_relaxed_u32(lldst + ((size_t)((u >> 3) * NBP + j) * 8 + (u & 7)) * 2,
-                         *reinterpret_cast<const unsigned int*>(&pk) | fword);
-        }
+        // publish: the 8 units of this warp (one k-chunk) x column j form one 16-byte chunk of the operand
+        // tile; they sit in the 8 lanes that share this gate index.  Assemble the chunk with a 3-level
+        // butterfly and let the ul_w == 0 lane issue ONE 16-byte store (atomic w.r.t. the readers' 16-byte
+        // loads: no half-updated chunks, 8x fewer L2 write transactions than per-pair 4-byte stores).
+        const unsigned int ulw = (unsigned int)lane >> 2;      // unit within the warp, 0..7
+        const float hp = __shfl_xor_sync(0xffffffffu, h, 4);
+        const __half2 pk = (ulw & 1) ? __floats2half2_rn(hp, h) : __floats2half2_rn(h, hp);
+        const unsigned int w1 = *reinterpret_cast<const unsigned int*>(&pk) | fword;
+        const unsigned int w1o = __shfl_xor_sync(0xffffffffu, w1, 8);
+        const unsigned int d0 = (ulw & 2) ? w1o : w1, d1 = (ulw & 2) ? w1 : w1o;
+        const unsigned int e0 = __shfl_xor_sync(0xffffffffu, d0, 16), e1 = __shfl_xor_sync(0xffffffffu, d1, 16);
+        if (ulw == 0)
+          st_relaxed_v4(lldst + (size_t)((u >> 3) * NBP + j) * 16, make_uint4(d0, d1, e0, e1));
       }
       if (tid == 0) REC_TRACE(11);
       // layer output (plain stores, not needed by the other CTAs) and the prefetch two steps ahead are issued
@@ -398,6 +407,11 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
         // gather h_t of the whole group (all nrb producers) into the smem operand tile: spin on the flag bits
         uint4 v[MAXCH];
         unsigned int pending = want_mask;
+        if (p.poll_delay > 0) {   // a poll issued before the other CTAs' stores reach L2 costs a full round trip
+          const long long t_go = clock64() + p.poll_delay;
+          while (clock64() < t_go) {
+          }
+        }
         while (pending) {
 #pragma unroll
           for (int i = 0; i < MAXCH; ++i)
@@ -505,6 +519,8 @@ extern "C" void onssen_blstm_rec_set_trace(void* device_buf_64_int64) {
   g_trace_ptr = (long long*)device_buf_64_int64;
 }
 
+extern "C" void onssen_blstm_rec_set_poll_delay(int cycles) { g_poll_delay = cycles < 0 ? 0 : cycles; }
+
 extern "C" size_t onssen_blstm_rec_workspace_bytes(int B, int H) {
   if (B <= 0 || H <= 0) return 0;
   const int Hp = hp_of(H);
@@ -557,6 +573,7 @@ static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int
   p.seed_lo = (unsigned int)mix;
   p.seed_hi = (unsigned int)(mix >> 32);
   p.trace = g_trace_ptr;
+  p.poll_delay = g_poll_delay;
   p.act_out = act_out; p.c_out = c_out; p.h_raw = (__half*)h_raw;
   const size_t hbuf_bytes = (size_t)2 * 2 * sp.S * p.Hp * sp.NBP * 2;
   if (workspace_bytes < 256 + hbuf_bytes) return ONSSEN_ERR_ARG;
