@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 OUT=../libonssen_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
+FLAGS="${ONSSEN_DEFS} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
 mkdir -p build
 pids=()
 for f in capi gemm_tc05 lstm_rec lstm_bwd pack loss stft extras backward; do

@@ -15,13 +15,20 @@ _, whh_p, _ = _lib.lstm_pack_layer(wf, wr, H, 2 * H, True, H)
 gates = torch.randn(T * B, 8 * Hp, device="cuda")
 y_h = torch.empty(T * B, 2 * Hp, device="cuda", dtype=torch.float16)
 ws = _lib.blstm_rec_workspace(B, H, "cuda")
-trace = torch.zeros(64, device="cuda", dtype=torch.int64)
+trace = torch.zeros(64 + 32 * 8, device="cuda", dtype=torch.int64)
 for tc in (True,):
     lib.onssen_blstm_rec_set_trace(ctypes.c_void_p(trace.data_ptr()))
     _lib.blstm_rec_fwd(gates, whh_p, B, T, H, y_h, None, 0.3, 1, 0, ws, tc)
     torch.cuda.synchronize()
     lib.onssen_blstm_rec_set_trace(None)
-    tr = trace.cpu().numpy().reshape(4, 16)
+    full = trace.cpu().numpy()
+    tr = full[:64].reshape(4, 16)
+    gt = full[64:64 + 19 * 8].reshape(19, 8)
+    t0 = gt[:, 0].min()
+    print('group trace step 102 (ns rel. to first mma-done): rb: mma_done, publish, gathered')
+    for rb in range(19):
+        print(f'   rb{rb:2d}: {gt[rb,0]-t0:6d} {gt[rb,1]-t0:6d} {gt[rb,2]-t0:6d}')
+    print(f'   publish spread {gt[:,1].max()-gt[:,1].min()} ns; last publish -> first gathered {gt[:,2].min()-gt[:,1].max()} ns; last gathered {gt[:,2].max()-gt[:,1].max()} ns')
     names = {3: "mma warp: h tile ready (bar3)", 4: "mma warp: issued+commit", 8: "gate: mma done", 9: "gate: tmem loaded",
              10: "gate: act+xchg written", 11: "gate: c/h + LL publish", 12: "gate: h gathered", 13: "gate: fenced+arrived"}
     for s in range(1, 4):
