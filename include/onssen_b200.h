@@ -246,6 +246,17 @@ int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const flo
                          void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
                          unsigned long long seed, unsigned long long offset, void* stream);
 
+/* Backward of onssen_loss_pit_l1_fwd w.r.t. the two masks (g [B] = upstream gradient, perm from the forward);
+ * d_mask_a / d_mask_b dense [B][N]. */
+int onssen_loss_pit_l1_bwd(const float* mask_a, const float* mask_b, long long mask_stride, const float* mag_mix,
+                           const float* mag_s1, const float* mag_s2, const float* cos_s1, const float* cos_s2,
+                           const int32_t* perm, const float* g, int B, int N, float* d_mask_a, float* d_mask_b,
+                           void* stream);
+/* sigmoid backward of the mask head (chimera.py:42): d_out/out batch-first [B][T][C] -> dz time-major [T*B][C]. */
+int onssen_sigmoid_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz, void* amax_bits_u32,
+                       void* stream);
+int onssen_add_inplace(float* a, const float* b, long long n, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Enhancement / phase-network variants of the path
  */

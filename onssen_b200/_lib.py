@@ -64,6 +64,9 @@ _SIGNATURES = {
                                            c_vp, c_sz, c_vp]),
     "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
+    "onssen_loss_pit_l1_bwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_sigmoid_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_add_inplace": (c_int, [c_vp, c_vp, c_ll, c_vp]),
     "onssen_mul_pack_f16": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_int, c_vp]),
     "onssen_pack_phase_input_f16": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_add_l2norm_pairs": (c_int, [c_vp, c_vp, c_ll, c_vp, c_vp]),
@@ -540,3 +543,35 @@ def blstm_rec_bwd(act_gates, dg16, c, dy, whh_t, scale2, B, T, H, dropout_p, see
     rc = lib.onssen_blstm_rec_bwd(_p(act_gates), _p(dg16), _p(c), _p(_req(dy, torch.float32)), _p(whh_t), _p(scratch),
                                   _p(scale2), B, T, H, float(dropout_p), int(seed), int(offset), _stream())
     _check(rc, "onssen_blstm_rec_bwd")
+
+
+def loss_pit_l1_bwd(mask_a, mask_b, mask_stride, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2, perm, g):
+    lib = load()
+    B = mag_mix.shape[0]
+    N = mag_mix.numel() // B
+    da = torch.empty(mag_mix.shape, device=mag_mix.device, dtype=torch.float32)
+    db = torch.empty(mag_mix.shape, device=mag_mix.device, dtype=torch.float32)
+    rc = lib.onssen_loss_pit_l1_bwd(_p(mask_a), _p(mask_b), mask_stride, _p(mag_mix), _p(mag_s1), _p(mag_s2), _p(cos_s1),
+                                    _p(cos_s2), _p(perm), _p(_req(g.float().contiguous(), torch.float32)), B, N, _p(da),
+                                    _p(db), _stream())
+    _check(rc, "onssen_loss_pit_l1_fwd")
+    return da, db
+
+
+def sigmoid_bwd(d_out, out):
+    lib = load()
+    B, T = out.shape[0], out.shape[1]
+    C = out.numel() // (B * T)
+    dz = torch.empty(T * B, C, device=out.device, dtype=torch.float32)
+    amax = torch.empty(1, device=out.device, dtype=torch.int32)
+    _check(lib.onssen_sigmoid_bwd(_p(_req(d_out, torch.float32)), _p(_req(out, torch.float32)), B, T, C, _p(dz), _p(amax),
+                                  _stream()), "onssen_sigmoid_bwd")
+    scale2 = torch.empty(2, device=out.device, dtype=torch.float32)
+    _check(lib.onssen_scale_from_amax_bits(_p(amax), 1024.0, _p(scale2), _stream()), "onssen_scale_from_amax_bits")
+    return dz, scale2
+
+
+def add_inplace(a, b):
+    _check(load().onssen_add_inplace(_p(_req(a, torch.float32)), _p(_req(b, torch.float32)), a.numel(), _stream()),
+           "onssen_add_inplace")
+    return a

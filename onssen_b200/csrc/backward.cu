@@ -234,10 +234,87 @@ __global__ void unpack_lstm_grad_kernel(const float* __restrict__ gp, int H, int
   }
 }
 
+// d/d mask of the PIT-L1 mask loss (loss_chimera.py:25-29,53-57): perm[b]==0 pairs (A,s1),(B,s2), else swapped.
+__global__ void pit_l1_bwd_kernel(const float* __restrict__ mask_a, const float* __restrict__ mask_b, long long mstride,
+                                  const float* __restrict__ mix, const float* __restrict__ s1,
+                                  const float* __restrict__ s2, const float* __restrict__ c1,
+                                  const float* __restrict__ c2, const int32_t* __restrict__ perm,
+                                  const float* __restrict__ g, int B, long long N, float* __restrict__ d_a,
+                                  float* __restrict__ d_b) {
+  const long long total = (long long)B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / N);
+    const float m = mix[i];
+    float t1 = s1[i], t2 = s2[i];
+    if (c1 != nullptr) {
+      t1 = fminf(m, fmaxf(t1 * c1[i], 0.f));
+      t2 = fminf(m, fmaxf(t2 * c2[i], 0.f));
+    }
+    const bool sw = perm[b] != 0;
+    const float ea = mask_a[i * mstride] * m - (sw ? t2 : t1);
+    const float eb = mask_b[i * mstride] * m - (sw ? t1 : t2);
+    const float gb = g[b] * m;
+    d_a[i] = ea > 0.f ? gb : (ea < 0.f ? -gb : 0.f);      // torch.abs backward: sign(x), 0 at 0
+    d_b[i] = eb > 0.f ? gb : (eb < 0.f ? -gb : 0.f);
+  }
+}
+
+// sigmoid backward + layout change: d_out / out batch-first [B][T][C]; dz time-major [T*B][C]
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int B, int T, int C,
+                                   float* __restrict__ dz, unsigned int* __restrict__ amax_bits) {
+  const long long total = (long long)B * T * C;
+  float am = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bt = i / C;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float o = out[i];
+    const float v = d_out[i] * o * (1.0f - o);
+    dz[((long long)t * B + b) * C + c] = v;
+    am = fmaxf(am, fabsf(v));
+  }
+  am = warp_max(am);
+  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_uint(am));
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    a[i] += b[i];
+}
+
 }  // namespace
 }  // namespace onssen
 
 using namespace onssen;
+
+extern "C" int onssen_loss_pit_l1_bwd(const float* mask_a, const float* mask_b, long long mask_stride,
+                                      const float* mag_mix, const float* mag_s1, const float* mag_s2,
+                                      const float* cos_s1, const float* cos_s2, const int32_t* perm, const float* g,
+                                      int B, int N, float* d_mask_a, float* d_mask_b, void* stream) {
+  if (!mask_a || !mask_b || !mag_mix || !mag_s1 || !mag_s2 || !perm || !g || !d_mask_a || !d_mask_b) return ONSSEN_ERR_ARG;
+  if ((cos_s1 == nullptr) != (cos_s2 == nullptr)) return ONSSEN_ERR_ARG;
+  pit_l1_bwd_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
+      mask_a, mask_b, mask_stride, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2, perm, g, B, N, d_mask_a, d_mask_b);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_sigmoid_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz,
+                                  void* amax_bits_u32, void* stream) {
+  if (!d_out || !out || !dz || !amax_bits_u32) return ONSSEN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(amax_bits_u32, 0, 4, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+  sigmoid_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, s>>>(d_out, out, B, T, C, dz,
+                                                                        (unsigned int*)amax_bits_u32);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_add_inplace(float* a, const float* b, long long n, void* stream) {
+  if (!a || !b || n <= 0) return ONSSEN_ERR_ARG;
+  add_inplace_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n);
+  return ONSSEN_CHECK_LAUNCH();
+}
 
 extern "C" int onssen_amax_scale(const float* x, long long n, float target, void* scratch_u32, float* scale2,
                                  void* stream) {

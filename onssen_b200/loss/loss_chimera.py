@@ -17,11 +17,27 @@ def _mask_args(mask_A, mask_B):
     return mask_A, mask_B, stride
 
 
+class _PitL1(torch.autograd.Function):
+    """PIT L1 mask loss with a hand-written backward (sign(mask*mix - target) * mix under the chosen permutation)."""
+
+    @staticmethod
+    def forward(ctx, mask_A, mask_B, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2):
+        ma, mb, stride = _mask_args(mask_A, mask_B)
+        out, perm = _lib.loss_pit_l1_fwd(ma, mb, stride, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2)
+        ctx.save_for_backward(ma, mb, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2, perm)
+        ctx.stride = stride
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ma, mb, mix, s1, s2, c1, c2, perm = ctx.saved_tensors
+        da, db = _lib.loss_pit_l1_bwd(ma, mb, ctx.stride, mix, s1, s2, c1, c2, perm, g)
+        return da, db, None, None, None, None, None
+
+
 def _pit(mask_A, mask_B, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None):
-    mask_A, mask_B, stride = _mask_args(mask_A, mask_B)
-    c = lambda t: None if t is None else t.float().contiguous()
-    out, _ = _lib.loss_pit_l1_fwd(mask_A, mask_B, stride, c(mag_mix), c(mag_s1), c(mag_s2), c(cos_s1), c(cos_s2))
-    return out
+    c = lambda t: None if t is None else t.detach().float().contiguous()
+    return _PitL1.apply(mask_A, mask_B, c(mag_mix), c(mag_s1), c(mag_s2), c(cos_s1), c(cos_s2))
 
 
 def loss_chimera_msa(output, label):

@@ -1,40 +1,138 @@
-"""Training path of the deep-clustering stack: forward that saves the BPTT state and a hand-written backward
+"""Training path of the BLSTM models: forward passes that save the BPTT state and hand-written backwards
 (no autograd graph of torch ops; every step below is a C-ABI call into libonssen_b200.so).
 
 Replaces what `loss_avg.backward()` (/root/reference/onssen/utils/train.py:82) gets from cuDNN/cuBLAS autograd
-for deep_clustering.py:34-42: F.normalize backward -> head dgrad/wgrad (tcgen05 GEMMs on scaled fp16 copies) ->
-BatchNorm backward -> per layer BPTT (one launch per step) + W_ih / W_hh / bias gradients (tcgen05 GEMMs
-contracting over all (t,b)) + dgrad to the layer below."""
+for deep_clustering.py:34-42 and chimera.py:35-45: F.normalize / sigmoid backward -> head dgrad/wgrad (tcgen05
+GEMMs on scaled fp16 copies) -> BatchNorm backward -> per layer BPTT (one launch per step) + W_ih / W_hh / bias
+gradients (tcgen05 GEMMs contracting over all (t,b)) + dgrad to the layer below."""
 import torch
 
 from .. import _lib
 from ._blstm import _next_seed, lstm_layer_params, pack_lstm
 
 
-def dc_forward_train(model, x):
-    rnn, bn = model.rnn, model.bn
-    B, T, F = x.shape
-    H, L, D = rnn.hidden_size, rnn.num_layers, model.embedding_dim
+# ------------------------------------------------------------------------------------------------ shared pieces
+def blstm_forward_train(rnn, cache, x, training, last_f32):
+    """Returns (layers, y_last) where y_last is fp32 [M][2Hp] (last_f32) or fp16; layers hold the BPTT state."""
+    B, T, _ = x.shape
+    H, L = rnn.hidden_size, rnn.num_layers
     Hp, M = _lib.hp_of(H), T * B
     params = [p for l in range(L) for d in lstm_layer_params(rnn, l) for p in d]
-    packed = model._rnn_cache.get(params, lambda: pack_lstm(rnn))
+    packed = cache.get(params, lambda: pack_lstm(rnn))
     a = _lib.pack_input_f16(x.contiguous())
     ws = _lib.blstm_rec_workspace(B, H, x.device)
-    layers, y_f = [], None
+    layers, y_h, y_f = [], None, None
     for l in range(L):
         wih_p, whh_p, bias_p = packed[l]
         gates = torch.empty(M, 8 * Hp, device=x.device, dtype=torch.float32)
         _lib.gemm_f16(a, wih_p, bias_p, gates, M, 8 * Hp, a.shape[1], 8 * Hp)
         last = l == L - 1
-        p = float(rnn.dropout) if (model.training and not last) else 0.0
+        p = float(rnn.dropout) if (training and not last) else 0.0
         seed = _next_seed() if p > 0 else 0
-        y_h = None if last else torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float16)
-        y_f = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float32) if last else None
+        y_h = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float16) if (not last or not last_f32) else None
+        y_f = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float32) if (last and last_f32) else None
         c = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float32)
-        h_raw = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float16) if (last or p > 0) else None
+        need_raw = p > 0 or y_h is None
+        h_raw = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float16) if need_raw else None
         _lib.blstm_rec_fwd_train(gates, whh_p, B, T, H, y_h, y_f, c, h_raw, p, seed, l, ws)
         layers.append(dict(a_in=a, gates=gates, c=c, h16=h_raw if h_raw is not None else y_h, p=p, seed=seed))
         a = y_h
+    return layers, packed, (y_f if last_f32 else y_h)
+
+
+def linear_backward(dz32, sc, a_in_h, w_p, N, H, grads, name):
+    """Linear(2H -> N) on the padded BLSTM-output layout: dz32 [M][N] fp32 (time-major), sc = scale2 of dz32,
+    a_in_h fp16 [M][2Hp] the layer's input, w_p fp16 [N][2Hp]. Fills grads[name.weight/bias]; returns dA [M][2Hp]."""
+    M = dz32.shape[0]
+    Hp, Mp = _lib.hp_of(H), _lib.pad64(M)
+    dz_n, dz_t = _lib.cast_transpose_f16(dz32, sc)
+    grads[name + ".bias"] = _lib.colsum(dz32)
+    aT = _lib.transpose_shift_f16(a_in_h, 0, 2 * Hp)
+    dWp = torch.empty(N, 2 * Hp, device=dz32.device, dtype=torch.float32)
+    _lib.gemm_f16_ex(dz_t, aT, None, dWp, N, 2 * Hp, Mp, 2 * Hp, out_scale=sc[1:])
+    grads[name + ".weight"] = _lib.unpack_linear_grad(dWp, N, 2 * H, True, H)
+    wT = _lib.transpose_shift_f16(w_p, 0, 2 * Hp)
+    dA = torch.empty(M, 2 * Hp, device=dz32.device, dtype=torch.float32)
+    _lib.gemm_f16_ex(dz_n, wT, None, dA, M, 2 * Hp, dz_n.shape[1], 2 * Hp, out_scale=sc[1:])
+    return dA
+
+
+def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None):
+    H, L = rnn.hidden_size, rnn.num_layers
+    Hp, M = _lib.hp_of(H), T * B
+    Mp = _lib.pad64(M)
+    dev = dY.device
+    for l in reversed(range(L)):
+        done_before = set(grads)
+        lay = layers[l]
+        wih_p = packed[l][0]
+        (wf, wr) = lstm_layer_params(rnn, l)
+        sc = _lib.amax_scale(dY)
+        dg16 = torch.empty(M, 8 * Hp, device=dev, dtype=torch.float16)
+        whh_t = _lib.lstm_pack_whh_t(wf[1], wr[1], H)
+        _lib.blstm_rec_bwd(lay["gates"], dg16, lay["c"], dY, whh_t, sc, B, T, H, lay["p"], lay["seed"], l)
+        dG32 = lay["gates"]                      # now the fp32 pre-activation gradients
+        inv = sc[1:]
+        gb = _lib.colsum(dG32)                   # [8Hp], permuted
+        kp_in = lay["a_in"].shape[1]
+        I_l = rnn.input_size if l == 0 else 2 * H
+        dgT = _lib.transpose_shift_f16(dg16, 0, 8 * Hp)
+        xT = _lib.transpose_shift_f16(lay["a_in"], 0, kp_in)
+        dWih_p = torch.empty(8 * Hp, kp_in, device=dev, dtype=torch.float32)
+        _lib.gemm_f16_ex(dgT, xT, None, dWih_p, 8 * Hp, kp_in, Mp, kp_in, out_scale=inv)
+        for d, suf in enumerate(("", "_reverse")):
+            grads[f"{prefix}weight_ih_l{l}{suf}"] = _lib.unpack_lstm_grad(dWih_p, H, I_l, l > 0, H if l > 0 else 0, d)
+            gbd = _lib.unpack_lstm_grad(gb, H, 1, False, 0, d, Kp=1).view(4 * H)
+            grads[f"{prefix}bias_ih_l{l}{suf}"] = gbd
+            grads[f"{prefix}bias_hh_l{l}{suf}"] = gbd
+            hT = _lib.transpose_shift_f16(lay["h16"], d * Hp, Hp, shift=B if d == 0 else -B)
+            dWhh_p = torch.empty(4 * Hp, Hp, device=dev, dtype=torch.float32)
+            _lib.gemm_f16_ex(dgT[d * 4 * Hp:(d + 1) * 4 * Hp], hT, None, dWhh_p, 4 * Hp, Hp, Mp, Hp, out_scale=inv)
+            grads[f"{prefix}weight_hh_l{l}{suf}"] = _lib.unpack_lstm_grad(dWhh_p, H, H, False, 0, 0)
+        if l > 0:
+            wihT = _lib.transpose_shift_f16(wih_p, 0, kp_in)
+            dX = torch.empty(M, kp_in, device=dev, dtype=torch.float32)
+            _lib.gemm_f16_ex(dg16, wihT, None, dX, M, kp_in, 8 * Hp, kp_in, out_scale=inv)
+            dY = dX
+        lay["gates"] = None
+        if on_grads is not None:
+            # bias_ih / bias_hh share one tensor: reduce it once
+            on_grads({k: v for k, v in grads.items() if k not in done_before and "bias_hh" not in k})
+    return grads
+
+
+class _ModelFunction(torch.autograd.Function):
+    """outputs = model(x) with a hand-written backward; `params` only carries the autograd edges."""
+
+    @staticmethod
+    def forward(ctx, model, fwd, bwd, x, *params):
+        outs, saved = fwd(model, x)
+        ctx.model, ctx.saved, ctx.bwd = model, saved, bwd
+        ctx.names = [n for n, _ in model.named_parameters()]
+        return outs if isinstance(outs, tuple) else outs
+
+    @staticmethod
+    def backward(ctx, *d_outs):
+        sync = getattr(ctx.model, "grad_sync", None)
+        grads = ctx.bwd(ctx.model, ctx.saved, [None if d is None else d.contiguous() for d in d_outs],
+                        None if sync is None else sync.reduce_bucket)
+        if sync is not None:
+            sync.wait()
+        ctx.saved = None
+        return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+def run_model(model, fwd, bwd, x):
+    return _ModelFunction.apply(model, fwd, bwd, x, *[p for _, p in model.named_parameters()])
+
+
+# ------------------------------------------------------------------------------------------------ deep clustering
+def dc_forward_train(model, x):
+    rnn, bn = model.rnn, model.bn
+    B, T, F = x.shape
+    H, D = rnn.hidden_size, model.embedding_dim
+    M = T * B
+    layers, packed, y_f = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=True)
     a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
                                             bn.running_var, bn.eps, bn.momentum, True, save_stats=True)
     bn.num_batches_tracked += 1
@@ -48,90 +146,71 @@ def dc_forward_train(model, x):
     return emb, saved
 
 
-def dc_backward(model, saved, d_emb, on_grads=None):
+def dc_backward(model, saved, d_outs, on_grads=None):
     """on_grads(dict) is called with each group of gradients as soon as it is final (head+BN, then every BLSTM
     layer from the top): the hook point for the overlapped data-parallel all-reduce (utils/ddp.py)."""
+    d_emb, = d_outs
     rnn, bn = model.rnn, model.bn
     B, T, F = saved["shape"]
-    H, L, D = rnn.hidden_size, rnn.num_layers, model.embedding_dim
-    Hp, M, N = _lib.hp_of(H), T * B, F * D
-    Mp = _lib.pad64(M)
-    dev = d_emb.device
+    H, D = rnn.hidden_size, model.embedding_dim
+    M, N = T * B, F * D
     grads = {}
-    f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
-
-    # ---- F.normalize + fc_dc
     dz32, sc = _lib.normalize_bwd(d_emb, saved["emb"], saved["inv_norm"])
-    dz_n, dz_t = _lib.cast_transpose_f16(dz32, sc)
-    grads["fc_dc.bias"] = _lib.colsum(dz32)
-    ahT = _lib.transpose_shift_f16(saved["a_h"], 0, 2 * Hp)
-    dWp = f32(N, 2 * Hp)
-    _lib.gemm_f16_ex(dz_t, ahT, None, dWp, N, 2 * Hp, Mp, 2 * Hp, out_scale=sc[1:])
-    grads["fc_dc.weight"] = _lib.unpack_linear_grad(dWp, N, 2 * H, True, H)
-    wT = _lib.transpose_shift_f16(saved["w_p"], 0, 2 * Hp)
-    dA = f32(M, 2 * Hp)
-    _lib.gemm_f16_ex(dz_n, wT, None, dA, M, 2 * Hp, dz_n.shape[1], 2 * Hp, out_scale=sc[1:])
-    del dz32, dz_n, dz_t
-    # ---- BatchNorm1d
+    dA = linear_backward(dz32, sc, saved["a_h"], saved["w_p"], N, H, grads, "fc_dc")
+    del dz32
     dY, grads["bn.weight"], grads["bn.bias"] = _lib.bn_backward(dA, saved["y_f"], M, H, bn.weight.detach(),
                                                                 saved["mean"], saved["invstd"])
     if on_grads is not None:
         on_grads(dict(grads))
-    # ---- BLSTM, top layer first
-    for l in reversed(range(L)):
-        done_before = set(grads)
-        lay = saved["layers"][l]
-        wih_p, _, _ = saved["packed"][l]
-        (wf, wr) = lstm_layer_params(rnn, l)
-        sc = _lib.amax_scale(dY)
-        dg16 = torch.empty(M, 8 * Hp, device=dev, dtype=torch.float16)
-        whh_t = _lib.lstm_pack_whh_t(wf[1], wr[1], H)
-        _lib.blstm_rec_bwd(lay["gates"], dg16, lay["c"], dY, whh_t, sc, B, T, H, lay["p"], lay["seed"], l)
-        dG32 = lay["gates"]                      # now the fp32 pre-activation gradients
-        inv = sc[1:]
-        gb = _lib.colsum(dG32)                   # [8Hp], permuted
-        kp_in = lay["a_in"].shape[1]
-        I_l = rnn.input_size if l == 0 else 2 * H
-        dgT = _lib.transpose_shift_f16(dg16, 0, 8 * Hp)
-        xT = _lib.transpose_shift_f16(lay["a_in"], 0, kp_in)
-        dWih_p = f32(8 * Hp, kp_in)
-        _lib.gemm_f16_ex(dgT, xT, None, dWih_p, 8 * Hp, kp_in, Mp, kp_in, out_scale=inv)
-        for d, suf in enumerate(("", "_reverse")):
-            grads[f"rnn.weight_ih_l{l}{suf}"] = _lib.unpack_lstm_grad(dWih_p, H, I_l, l > 0, H if l > 0 else 0, d)
-            gbd = _lib.unpack_lstm_grad(gb, H, 1, False, 0, d, Kp=1).view(4 * H)
-            grads[f"rnn.bias_ih_l{l}{suf}"] = gbd
-            grads[f"rnn.bias_hh_l{l}{suf}"] = gbd
-            hT = _lib.transpose_shift_f16(lay["h16"], d * Hp, Hp, shift=B if d == 0 else -B)
-            dWhh_p = f32(4 * Hp, Hp)
-            _lib.gemm_f16_ex(dgT[d * 4 * Hp:(d + 1) * 4 * Hp], hT, None, dWhh_p, 4 * Hp, Hp, Mp, Hp, out_scale=inv)
-            grads[f"rnn.weight_hh_l{l}{suf}"] = _lib.unpack_lstm_grad(dWhh_p, H, H, False, 0, 0)
-        if l > 0:
-            wihT = _lib.transpose_shift_f16(wih_p, 0, kp_in)
-            dX = f32(M, kp_in)
-            _lib.gemm_f16_ex(dg16, wihT, None, dX, M, kp_in, 8 * Hp, kp_in, out_scale=inv)
-            dY = dX
-        lay["gates"] = None
-        if on_grads is not None:
-            # bias_ih / bias_hh share one tensor: reduce it once
-            on_grads({k: v for k, v in grads.items() if k not in done_before and "bias_hh" not in k})
-    return grads
+    return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)
 
 
-class DCFunction(torch.autograd.Function):
-    """emb = deep_clustering(x) with a hand-written backward; `params` only carries the autograd edges."""
+# ------------------------------------------------------------------------------------------------ chimera(++)
+def chimera_forward_train(model, x):
+    rnn = model.rnn
+    B, T, F = x.shape
+    H, D, S = rnn.hidden_size, model.embedding_dim, model.num_speaker
+    M = T * B
+    layers, packed, y_h = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=False)
+    wdc = model._dc_cache.get([model.fc_dc.weight], lambda: _lib.pack_linear_f16(model.fc_dc.weight, True, H))
+    wmi = model._mi_cache.get([model.fc_mi.weight], lambda: _lib.pack_linear_f16(model.fc_mi.weight, True, H))
+    emb = torch.empty(B, T, F, D, device=x.device, dtype=torch.float32)
+    inv_norm = torch.empty(B, T, F, device=x.device, dtype=torch.float32)
+    _lib.gemm_f16_ex(y_h, wdc, model.fc_dc.bias.detach(), emb, M, F * D, y_h.shape[1], F * D, epi=3, group=D,
+                     remap_inner=B, remap_outer=T, inv_norm=inv_norm)
+    masks = torch.empty(B, T, F, S, device=x.device, dtype=torch.float32)
+    _lib.gemm_f16(y_h, wmi, model.fc_mi.bias.detach(), masks, M, F * S, y_h.shape[1], F * S, epi=1, remap_inner=B,
+                  remap_outer=T)
+    saved = dict(layers=layers, packed=packed, y_h=y_h, emb=emb, inv_norm=inv_norm, masks=masks, wdc=wdc, wmi=wmi,
+                 shape=(B, T, F))
+    return (emb, masks), saved
 
-    @staticmethod
-    def forward(ctx, model, x, *params):
-        emb, saved = dc_forward_train(model, x)
-        ctx.model, ctx.saved = model, saved
-        ctx.names = [n for n, _ in model.named_parameters()]
-        return emb
 
-    @staticmethod
-    def backward(ctx, d_emb):
-        sync = getattr(ctx.model, "grad_sync", None)
-        grads = dc_backward(ctx.model, ctx.saved, d_emb.contiguous(), None if sync is None else sync.reduce_bucket)
-        if sync is not None:
-            sync.wait()
-        ctx.saved = None
-        return (None, None) + tuple(grads[n] for n in ctx.names)
+def chimera_backward(model, saved, d_outs, on_grads=None):
+    d_emb, d_masks = d_outs
+    rnn = model.rnn
+    B, T, F = saved["shape"]
+    H, D, S = rnn.hidden_size, model.embedding_dim, model.num_speaker
+    M = T * B
+    dev = saved["emb"].device
+    grads = {}
+    dY = None
+    if d_emb is not None:
+        dz32, sc = _lib.normalize_bwd(d_emb, saved["emb"], saved["inv_norm"])
+        dY = linear_backward(dz32, sc, saved["y_h"], saved["wdc"], F * D, H, grads, "fc_dc")
+        del dz32
+    else:
+        grads["fc_dc.weight"] = torch.zeros_like(model.fc_dc.weight)
+        grads["fc_dc.bias"] = torch.zeros_like(model.fc_dc.bias)
+    if d_masks is not None:
+        dzm, scm = _lib.sigmoid_bwd(d_masks, saved["masks"])
+        dYm = linear_backward(dzm, scm, saved["y_h"], saved["wmi"], F * S, H, grads, "fc_mi")
+        dY = dYm if dY is None else _lib.add_inplace(dY, dYm)
+    else:
+        grads["fc_mi.weight"] = torch.zeros_like(model.fc_mi.weight)
+        grads["fc_mi.bias"] = torch.zeros_like(model.fc_mi.bias)
+    if dY is None:
+        dY = torch.zeros(M, 2 * _lib.hp_of(H), device=dev, dtype=torch.float32)
+    if on_grads is not None:
+        on_grads(dict(grads))
+    return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)

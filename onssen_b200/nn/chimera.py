@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward, require_no_grad
+from ._blstm import PackCache, blstm_forward
 
 
 class chimera(nn.Module):
@@ -24,7 +24,10 @@ class chimera(nn.Module):
     def forward(self, input):
         assert len(input) == 1, "There must be one tensor in the input for the chimera network"
         x = input[0].float()
-        require_no_grad("chimera", x, self.fc_dc.weight)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from ._train import chimera_backward, chimera_forward_train, run_model
+            embedding, masks = run_model(self, chimera_forward_train, chimera_backward, x)
+            return [embedding, masks[:, :, :, 0], masks[:, :, :, 1]]
         B, T, F = x.shape
         H, D, S = self.hidden_dim, self.embedding_dim, self.num_speaker
         M = T * B

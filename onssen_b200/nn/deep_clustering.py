@@ -29,8 +29,8 @@ class deep_clustering(nn.Module):
             if not self.training:
                 raise NotImplementedError("deep_clustering: gradients are implemented for train() mode "
                                           "(batch-statistics BatchNorm), call model.train()")
-            from ._train import DCFunction
-            return [DCFunction.apply(self, x, *[p for _, p in self.named_parameters()])]
+            from ._train import dc_backward, dc_forward_train, run_model
+            return [run_model(self, dc_forward_train, dc_backward, x)]
         B, T, F = x.shape
         H, D = self.hidden_dim, self.embedding_dim
         M = T * B

@@ -101,6 +101,13 @@ def main():
             e, ma, mb = ch([tt(feat)])
             l_msa = onssen.loss.loss_chimera_msa([e, ma, mb], [tt(oh), tt(mix), tt(mag1), tt(mag2)])
             l_psa = onssen.loss.loss_chimera_psa([e, ma, mb], [tt(oh), tt(mix), tt(mag1), tt(mag2), tt(cos1), tt(cos2)])
+        # gradients of torch.mean(loss_chimera_psa) (train mode == eval mode here: no BN, dropout 0)
+        ch.zero_grad()
+        e_g, ma_g, mb_g = ch([tt(feat)])
+        torch.mean(onssen.loss.loss_chimera_psa([e_g, ma_g, mb_g], [tt(oh), tt(mix), tt(mag1), tt(mag2), tt(cos1),
+                                                                    tt(cos2)])).backward()
+        np.savez_compressed(os.path.join(out_dir, f"chimeragrad_{name}.npz"),
+                            **{"g:" + k: v.grad.detach().numpy().copy() for k, v in ch.named_parameters()})
         np.savez_compressed(os.path.join(out_dir, f"chimera_{name}.npz"), cfg=np.array([B, T, F, H, L, D]), feature=feat,
                             one_hot=oh, mag_mix=mix, mag_s1=mag1, mag_s2=mag2, cos_s1=cos1, cos_s2=cos2,
                             emb=e.numpy(), mask_a=ma.numpy(), mask_b=mb.numpy(), loss_msa=l_msa.numpy(),

@@ -68,3 +68,23 @@ def test_training_step_reduces_loss(cuda_device):
         opt.step()
         losses.append(loss.item())
     assert np.isfinite(losses).all() and losses[-1] < 0.9 * losses[0], losses
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_chimera_gradients_vs_reference(cuda_device, name):
+    import onssen_b200 as ob
+    p, g = load_golden(f"chimera_{name}.npz")
+    gz = np.load(f"tests/golden/chimeragrad_{name}.npz")
+    B, T, F, H, L, D = [int(v) for v in g["cfg"]]
+    model = ob.nn.chimera(F, H, L, D, dropout=0.0).to(cuda_device).train()
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()}, strict=False)
+    cu = lambda a: torch.from_numpy(a).to(cuda_device)
+    out = model([cu(g["feature"])])
+    lab = [cu(g[k]) for k in ("one_hot", "mag_mix", "mag_s1", "mag_s2", "cos_s1", "cos_s2")]
+    torch.mean(ob.loss.loss_chimera_psa(out, lab)).backward()
+    worst = 0.0
+    for k, v in model.named_parameters():
+        e = rel_err(v.grad.cpu().numpy(), gz["g:" + k])
+        worst = max(worst, e)
+        assert e < 3e-2, (k, e)
+    print("chimera++ worst relative gradient error", worst)
