@@ -46,7 +46,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -208,8 +208,8 @@ def run_gpu(args):
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for i in range(K):
-            ws, st = host_batches[i % nbatch]
-            lv = step([w.to(dev, non_blocking=True) for w in ws], st.to(dev, non_blocking=True)).item()
+            ws, st = host_batches[i % nbatch]             # pinned host waveforms -> H2D inside the timed region
+            lv = step([w.to(dev, non_blocking=True) for w in ws], st.to(dev, non_blocking=True)).item()   # D2H read
         f1.record()
         barrier()
         ms_e2e = torch.tensor([f0.elapsed_time(f1)], device=dev)
@@ -303,7 +303,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step figure")

@@ -78,3 +78,21 @@ def test_trainer_validate_and_tester_eval(cuda_device, tmp_path):
     rec = t.masked_istft(lab[0], lab[1], ones, lab[2].shape[2])
     mix = lab[2][0].sum(0)
     assert (rec[0, 0] - mix).abs().max().item() < 2e-4 * mix.abs().max().item() + 1e-4   # s1+s2 == mix up to int16 rounding
+
+
+def test_device_prefetcher_matches_inline_featurizer(cuda_device):
+    import onssen_b200 as ob
+    B, T = 2, 50
+    batches = []
+    for k in range(3):
+        utts = [O.synth_utterance(10 * k + i, 6000) for i in range(B)]
+        ws = [torch.from_numpy(np.stack([u[j] for u in utts])).pin_memory() for j in range(3)]
+        batches.append((ws[0], ws[1], ws[2], torch.tensor([k, 2 * k], dtype=torch.int32)))
+    got = list(ob.data.DevicePrefetcher(batches, "chimera++", 256, 64, T, 40, cuda_device))
+    assert len(got) == 3
+    for (inp, lab), item in zip(got, batches):
+        ri, rl = ob.data.featurize_batch(*[t.to(cuda_device) for t in item[:3]], "chimera++", 256, 64, T, 40,
+                                         crop_start=item[3])
+        torch.cuda.synchronize()
+        for a, b in zip(inp + lab, ri + rl):
+            assert torch.equal(a, b)
