@@ -27,12 +27,14 @@ template <int D, int TS, typename LT>
 __global__ void __launch_bounds__(DC_THREADS)
 loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ label,
                        const float* __restrict__ mag, int N, float* __restrict__ scratch) {
+  // only the tiles on or above the diagonal of the symmetric Gram are accumulated (tj >= ti); the final kernel
+  // counts off-diagonal tiles twice.  GT threads per group, NG groups split the points of a tile.
   constexpr int TG = D / TS;
-  constexpr int GT = TG * TG;
+  constexpr int GT = TG * (TG + 1) / 2;
   constexpr int NG = DC_THREADS / GT;
   constexpr int P = NG > 64 ? NG : 64;
   constexpr int R = D * D + D * 2 + 4;
-  static_assert(TG * TS == D && NG * GT == DC_THREADS, "unsupported D");
+  static_assert(TG * TS == D && NG >= 1, "unsupported D");
   extern __shared__ __align__(16) float sm[];
   float* a_s = sm;                 // [P][D]   s_n * e_n
   float* ma_s = a_s + P * D;       // [P][D]   m_n * s_n * e_n
@@ -46,10 +48,15 @@ loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ lab
   const int n_begin = chunk * DC_PTS_PER_CHUNK;
   const int n_end = min(N, n_begin + DC_PTS_PER_CHUNK);
   const int tid = threadIdx.x;
-  const int g = tid / GT;
+  const int g = tid / GT;          // g >= NG: idle in the accumulation (still stages data / syncs)
   const int lt = tid % GT;
-  const int ti = lt / TG;
-  const int tj = lt % TG;
+  int ti = 0, tj;
+  {
+    int rem = lt;
+    while (rem >= TG - ti) { rem -= TG - ti; ++ti; }
+    tj = ti + rem;
+  }
+  const bool diag = (ti == tj);
 
   float acc[TS][TS];
   float accy[TS][2];
@@ -82,7 +89,7 @@ loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ lab
                                                        e.z * s * m_s[pnt], e.w * s * m_s[pnt]);
     }
     __syncthreads();
-    for (int pnt = g; pnt < np; pnt += NG) {
+    for (int pnt = g; pnt < np && g < NG; pnt += NG) {
       float rv[TS], cv[TS];
       if constexpr ((TS & 1) == 0) {   // D*4 and TS*4 bytes are multiples of 8: 64-bit smem loads
 #pragma unroll
@@ -103,7 +110,7 @@ loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ lab
       for (int i = 0; i < TS; ++i)
 #pragma unroll
         for (int j = 0; j < TS; ++j) acc[i][j] = fmaf(rv[i], cv[j], acc[i][j]);
-      if (tj == 0) {
+      if (diag) {
         const float y0 = y_s[2 * pnt], y1 = y_s[2 * pnt + 1];
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
@@ -121,13 +128,17 @@ loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ lab
     }
     __syncthreads();
   }
-  // cross-group reduction in a fixed order (deterministic)
-  float* mine = red + g * R;
+  // cross-group reduction in a fixed order (deterministic); entries below the diagonal tiles stay zero
+  for (int i = tid; i < NG * R; i += DC_THREADS) red[i] = 0.f;
+  __syncthreads();
+  float* mine = red + (g < NG ? g : 0) * R;
+  if (g < NG) {
 #pragma unroll
   for (int i = 0; i < TS; ++i)
 #pragma unroll
     for (int j = 0; j < TS; ++j) mine[(ti * TS + i) * D + tj * TS + j] = acc[i][j];
-  if (tj == 0) {
+  }
+  if (diag && g < NG) {
 #pragma unroll
     for (int i = 0; i < TS; ++i) {
       mine[D * D + (ti * TS + i) * 2] = accy[i][0];
@@ -150,7 +161,7 @@ loss_dc_partial_kernel(const float* __restrict__ emb, const LT* __restrict__ lab
 
 template <int D, int TS>
 constexpr size_t dc_smem_bytes() {
-  constexpr int TG = D / TS, GT = TG * TG, NG = DC_THREADS / GT, P = NG > 64 ? NG : 64;
+  constexpr int TG = D / TS, GT = TG * (TG + 1) / 2, NG = DC_THREADS / GT, P = NG > 64 ? NG : 64;
   constexpr size_t tile = (size_t)(2 * P * D + 3 * P) * 4;
   constexpr size_t red = (size_t)NG * (D * D + D * 2 + 4) * 4;
   return tile > red ? tile : red;
@@ -228,7 +239,8 @@ __global__ void __launch_bounds__(256) loss_dc_reduce_kernel(const float* __rest
 
 // per-utterance: norms, l_b and sum(m)_b from the summed record (nchunk == 1 layout)
 __global__ void __launch_bounds__(256) loss_dc_final_kernel(const float* __restrict__ scratch, int nchunk, int D,
-                                                            int S, int fast_layout, float* __restrict__ l_out,
+                                                            int S, int fast_layout, int sym_ts,
+                                                            float* __restrict__ l_out,
                                                             float* __restrict__ msum_out) {
   const int b = blockIdx.x;
   // layout of one partial record
@@ -243,7 +255,9 @@ __global__ void __launch_bounds__(256) loss_dc_final_kernel(const float* __restr
     float v = 0.f;
     for (int c = 0; c < nchunk; ++c) v += base[(long long)c * R + i];
     if (i < nG) {
-      q[0] += (double)v * v;
+      // symmetric fast layout: only tiles with tile(col) >= tile(row) are stored; off-diagonal tiles count twice
+      const double w = (sym_ts > 0 && (i / D) / sym_ts < (i % D) / sym_ts) ? 2.0 : 1.0;
+      q[0] += w * (double)v * v;
     } else if (i < nG + nC) {
       q[1] += (double)v * v;
     } else if (i < nG + nC + nY) {
@@ -303,6 +317,8 @@ inline bool dc_fast_layout(const float* emb, int D, int S) {
   return D == 8 || D == 16 || D == 20 || D == 32 || D == 40 || D == 64;
 }
 
+inline int dc_tile_size(int D) { return (D == 20 || D == 40) ? 5 : 4; }   // TS of the fast kernels below
+
 template <typename LT>
 int dispatch_dc(const float* emb, const void* label, const float* mag, int B, int N, int D, int S,
                 float* scratch, cudaStream_t s, int* fast) {
@@ -335,8 +351,8 @@ int dispatch_dc(const float* emb, const void* label, const float* mag, int B, in
 template <int D, typename LT>
 __global__ void __launch_bounds__(256)
 loss_dc_bwd_kernel(const float* __restrict__ emb, const LT* __restrict__ label, const float* __restrict__ mag,
-                   const float* __restrict__ summed, int R, int msum_idx, const float* __restrict__ g_bb, int B,
-                   int N, float* __restrict__ d_emb) {
+                   const float* __restrict__ summed, int R, int msum_idx, int sym_ts,
+                   const float* __restrict__ g_bb, int B, int N, float* __restrict__ d_emb) {
   constexpr int GSZ = D <= 32 ? 32 : 64;
   constexpr int NG = 256 / GSZ;
   constexpr int P = 64;
@@ -353,7 +369,10 @@ loss_dc_bwd_kernel(const float* __restrict__ emb, const LT* __restrict__ label, 
   // norms of G and C (fp64 block reduction, same for every block of this utterance)
   {
     double q0 = 0.0, q1 = 0.0;
-    for (int i = tid; i < D * D; i += 256) q0 += (double)rec[i] * rec[i];
+    for (int i = tid; i < D * D; i += 256) {
+      const double w = (sym_ts > 0 && (i / D) / sym_ts < (i % D) / sym_ts) ? 2.0 : 1.0;   // see loss_dc_final_kernel
+      q0 += w * (double)rec[i] * rec[i];
+    }
     for (int i = tid; i < D * 2; i += 256) q1 += (double)rec[D * D + i] * rec[D * D + i];
     q0 = warp_sum(q0); q1 = warp_sum(q1);
     if ((tid & 31) == 0) { s_red[0][tid >> 5] = q0; s_red[1][tid >> 5] = q1; }
@@ -375,7 +394,8 @@ loss_dc_bwd_kernel(const float* __restrict__ emb, const LT* __restrict__ label, 
   float c0 = 0.f, c1 = 0.f;
   if (d < D) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) grow[k] = rec[d * D + k];
+    for (int k = 0; k < D; ++k)   // symmetric record: the entry lives in the tile on/above the diagonal
+      grow[k] = (sym_ts > 0 && d / sym_ts > k / sym_ts) ? rec[k * D + d] : rec[d * D + k];
     c0 = rec[D * D + d * 2];
     c1 = rec[D * D + d * 2 + 1];
   }
@@ -418,12 +438,12 @@ loss_dc_bwd_kernel(const float* __restrict__ emb, const LT* __restrict__ label, 
 
 template <typename LT>
 int dispatch_dc_bwd(const float* emb, const void* label, const float* mag, const float* summed, int R, int msum_idx,
-                    const float* g_bb, int B, int N, int D, float* d_emb, cudaStream_t s) {
+                    int sym_ts, const float* g_bb, int B, int N, int D, float* d_emb, cudaStream_t s) {
   dim3 grid((N + DC_PTS_PER_CHUNK - 1) / DC_PTS_PER_CHUNK, B);
 #define ONSSEN_DC_BWD(DD)                                                                                  \
   case DD:                                                                                                  \
-    loss_dc_bwd_kernel<DD, LT><<<grid, 256, 0, s>>>(emb, (const LT*)label, mag, summed, R, msum_idx, g_bb, B, N,  \
-                                                    d_emb);                                                    \
+    loss_dc_bwd_kernel<DD, LT><<<grid, 256, 0, s>>>(emb, (const LT*)label, mag, summed, R, msum_idx, sym_ts, g_bb, \
+                                                    B, N, d_emb);                                               \
     break;
   switch (D) {
     ONSSEN_DC_BWD(8) ONSSEN_DC_BWD(16) ONSSEN_DC_BWD(20) ONSSEN_DC_BWD(32) ONSSEN_DC_BWD(40) ONSSEN_DC_BWD(64)
@@ -500,7 +520,7 @@ extern "C" int onssen_loss_dc_fwd(const float* emb, const void* label, int label
   const int R = fast ? (D * D + D * 2 + 4) : (D * D + D * S + S * S + 1);
   float* summed = scratch + (long long)B * nchunk * (D * D + D * S + S * S + 4);   // behind the partial records
   loss_dc_reduce_kernel<<<dim3((R + 255) / 256, B), 256, 0, s>>>(scratch, nchunk, R, summed);
-  loss_dc_final_kernel<<<B, 256, 0, s>>>(summed, 1, D, S, fast, l, mag_sum);
+  loss_dc_final_kernel<<<B, 256, 0, s>>>(summed, 1, D, S, fast, fast ? dc_tile_size(D) : 0, l, mag_sum);
   if (loss_bb) loss_dc_outer_kernel<<<(B * B + 255) / 256, 256, 0, s>>>(l, mag_sum, B, loss_bb);
   return ONSSEN_CHECK_LAUNCH();
 }
@@ -515,11 +535,12 @@ extern "C" int onssen_loss_dc_bwd(const float* emb, const void* label, int label
   const bool fast = dc_fast_layout(emb, D, S);
   const int R = fast ? D * D + D * 2 + 4 : D * D + D * S + S * S + 1;
   const int mi = R - 1;
+  const int st = fast ? dc_tile_size(D) : 0;
   cudaStream_t s = (cudaStream_t)stream;
   switch (label_dtype) {
-    case ONSSEN_DT_F32: return dispatch_dc_bwd<float>(emb, label, mag, summed_record, R, mi, g_bb, B, N, D, d_emb, s);
-    case ONSSEN_DT_F64: return dispatch_dc_bwd<double>(emb, label, mag, summed_record, R, mi, g_bb, B, N, D, d_emb, s);
-    case ONSSEN_DT_U8: return dispatch_dc_bwd<uint8_t>(emb, label, mag, summed_record, R, mi, g_bb, B, N, D, d_emb, s);
+    case ONSSEN_DT_F32: return dispatch_dc_bwd<float>(emb, label, mag, summed_record, R, mi, st, g_bb, B, N, D, d_emb, s);
+    case ONSSEN_DT_F64: return dispatch_dc_bwd<double>(emb, label, mag, summed_record, R, mi, st, g_bb, B, N, D, d_emb, s);
+    case ONSSEN_DT_U8: return dispatch_dc_bwd<uint8_t>(emb, label, mag, summed_record, R, mi, st, g_bb, B, N, D, d_emb, s);
     default: return ONSSEN_ERR_ARG;
   }
 }
