@@ -33,7 +33,7 @@ using namespace tc05;
 constexpr int REC_GATE_WARPS = 8;
 constexpr int REC_THREADS = (REC_GATE_WARPS + 1) * 32;  // 8 gate warps + 1 control warp
 constexpr int TMEM_A_COL = 128;                         // first TMEM column of the resident W_hh slice
-constexpr int NACC = 4;   // independent accumulators (columns a*NBP): back-to-back MMAs into ONE accumulator
+constexpr int NACC = 2;   // independent accumulators (columns a*NBP): back-to-back MMAs into ONE accumulator
                           // serialise on the ~70-cycle accumulate latency when N is this small
 constexpr int TRACE_S0 = 100;
 long long* g_trace_ptr = nullptr;
@@ -234,15 +234,16 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
         // updates would chain every MMA behind ~10-cycle uniform-datapath adds
         uint64_t db0 = make_smem_desc(h_addr, NBP * 16, 128, 0);
         uint32_t ta0 = tmem_base + TMEM_A_COL;
-        for (int ks0 = 0; ks0 < ksteps; ks0 += 8) {
+        constexpr int UB = 19;   // k-steps per unrolled issue block (H=600: 38 = 2 blocks)
+        for (int ks0 = 0; ks0 < ksteps; ks0 += UB) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < UB; ++j) {
             if (ks0 + j < ksteps && leader)
               umma_f16_ts(tmem_base + (j % NACC) * NBP, ta0 + 8 * j, db0 + (uint64_t)j * DB_STEP, idesc,
                           (ks0 + j) >= NACC);
           }
-          ta0 += 64;           // 8 k-steps x (K=16 fp16 = 8 TMEM columns)
-          db0 += 8 * DB_STEP;
+          ta0 += 8 * UB;       // UB k-steps x (K=16 fp16 = 8 TMEM columns)
+          db0 += UB * DB_STEP;
         }
         if (leader) umma_commit(mbar);
         __syncwarp();
@@ -314,11 +315,10 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
         const int nacc = min(NACC, Hp / 16);   // accumulators actually written (tiny Hp: fewer k-steps)
 #pragma unroll
         for (int j = 0; j < NBH; ++j) {
-          const float a0 = __uint_as_float(v[0][j]);
-          const float a1 = nacc > 1 ? __uint_as_float(v[1][j]) : 0.f;
-          const float a2 = nacc > 2 ? __uint_as_float(v[2][j]) : 0.f;
-          const float a3 = nacc > 3 ? __uint_as_float(v[3][j]) : 0.f;
-          acc[j] = (a0 + a1) + (a2 + a3);
+          float a = __uint_as_float(v[0][j]);
+#pragma unroll
+          for (int q2 = 1; q2 < NACC; ++q2) a += (nacc > q2) ? __uint_as_float(v[q2][j]) : 0.f;
+          acc[j] = a;
         }
         if (tid == 0) REC_TRACE(9);
       } else {
