@@ -34,6 +34,15 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def rec_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the recurrent kernel from the committed
+    `ncu --set full` capture of this same command (profiles/r01_ncu_full_final.csv); None if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_rec_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clock/throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -268,7 +277,7 @@ def run_gpu(args):
             ach = alg_bytes / (rec_avg_ms * 1e-3) / 1e9
             roof = {"kernel": "blstm_rec_kernel (one launch = one BLSTM layer, both directions, T steps)",
                     "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": None, "peak_source": pk_src + " (burst copy bandwidth, kernel timed per launch)",
+                    "traffic": rec_traffic(), "peak_source": pk_src + " (burst copy bandwidth, kernel timed per launch)",
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": rec_avg_ms, "us_per_step": rec_avg_ms * 1e3 / T,
                     "share_of_step": float(np.sum(rec_ms)) / ms.item(),

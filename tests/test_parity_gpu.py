@@ -109,3 +109,27 @@ def test_deep_clustering_baseline_shape_vs_oracle(cuda_device):
     with torch.no_grad():
         emb_p, = model([inp[0][perm].contiguous()])
     assert (emb_p - emb[perm]).abs().max().item() < 5e-4   # batch-slice assignment changes only rounding order
+
+
+def test_chimera_pp_baseline_shape_vs_oracle(cuda_device):
+    """BASELINE cfg3 shape (chimera++ 4x600 BLSTM, mask + embed heads, PSA / W_MR loss, T=400) at a batch the
+    numpy oracle finishes in seconds; inputs from the device featurizer on seeded synthetic mixtures."""
+    import onssen_b200 as ob
+    B, T, F, H, L, D = 3, 400, 129, 600, 4, 20
+    torch.manual_seed(2)
+    model = ob.nn.chimera(F, H, L, D).to(cuda_device).eval()
+    utts = [O.synth_utterance(20 + i) for i in range(B)]
+    cu = lambda k: torch.from_numpy(np.stack([u[k] for u in utts])).to(cuda_device)
+    starts = torch.tensor([3, 50, 99], dtype=torch.int32)
+    with torch.no_grad():
+        inp, lab = ob.data.featurize_batch(cu(0), cu(1), cu(2), "chimera++", 256, 64, T, 40, crop_start=starts)
+        out = model(inp)
+        loss = ob.loss.loss_chimera_psa(out, lab)
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    ref = O.chimera_forward(params, [inp[0].cpu().numpy()], L)
+    loss_ref = O.loss_chimera_psa(ref, [t.cpu().numpy() for t in lab])
+    err_e = np.abs(out[0].cpu().numpy() - ref[0]).max()
+    err_m = max(np.abs(out[1].cpu().numpy() - ref[1]).max(), np.abs(out[2].cpu().numpy() - ref[2]).max())
+    rel = np.abs(loss.cpu().numpy() - loss_ref).max() / np.abs(loss_ref).max()
+    print(f"cfg3-shape parity: max|emb err|={err_e:.3e} max|mask err|={err_m:.3e} loss rel dev={rel:.3e}")
+    assert err_e < EMB_ATOL and err_m < 1e-3 and rel < LOSS_RTOL
