@@ -242,6 +242,10 @@ int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int
  * (the dropout mask is re-derived from seed/offset); scratch: onssen_blstm_rec_bwd_scratch_bytes(B, H) (cell
  * gradient carry + the per-step dG exchange buffer in B-fragment order), zeroed by the call. */
 size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H);
+/* 1 (default): one persistent cooperative launch per layer (W_hh^T resident in smem, flag-bit dG exchange; requires
+ * the scale passed to onssen_blstm_rec_bwd to keep |dG*scale| < 2, i.e. scale2 from a target <= 2^-4 * headroom);
+ * 0: one launch per time step (validation path). */
+void onssen_blstm_rec_bwd_set_persistent(int on);
 int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
                          void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
                          unsigned long long seed, unsigned long long offset, void* stream);
@@ -256,6 +260,16 @@ int onssen_loss_pit_l1_bwd(const float* mask_a, const float* mask_b, long long m
 int onssen_sigmoid_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz, void* amax_bits_u32,
                        void* stream);
 int onssen_add_inplace(float* a, const float* b, long long n, void* stream);
+/* relu backward with the same layout change as onssen_sigmoid_bwd (enhancement.py:49,51). */
+int onssen_relu_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz, void* amax_bits_u32,
+                    void* stream);
+/* backward of est = relu-output `pre` * sigmoid-output `mask` (enhancement.py:49-50), all time-major [M][F] (d_est with
+ * row pitch ld): dz_pre = d_est*mask*(pre>0), dz_mi = d_est*pre*mask*(1-mask); amax bit patterns of both in
+ * amax_bits_2xu32[0..1]. */
+int onssen_enhance_mid_bwd(const float* d_est, long long ld, const float* pre, const float* mask, long long M, int F,
+                           float* dz_pre, float* dz_mi, void* amax_bits_2xu32, void* stream);
+/* nn.MSELoss backward: d_a = 2 (a - b) / n * g[0]  (g = device scalar upstream gradient). */
+int onssen_loss_mse_bwd(const float* a, const float* b, long long n, const float* g, float* d_a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Enhancement / phase-network variants of the path

@@ -63,10 +63,14 @@ _SIGNATURES = {
     "onssen_blstm_rec_fwd_train": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_ull, c_ull,
                                            c_vp, c_sz, c_vp]),
     "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
+    "onssen_blstm_rec_bwd_set_persistent": (None, [c_int]),
     "onssen_blstm_rec_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
     "onssen_loss_pit_l1_bwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_vp]),
     "onssen_sigmoid_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "onssen_add_inplace": (c_int, [c_vp, c_vp, c_ll, c_vp]),
+    "onssen_relu_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_enhance_mid_bwd": (c_int, [c_vp, c_ll, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "onssen_loss_mse_bwd": (c_int, [c_vp, c_vp, c_ll, c_vp, c_vp, c_vp]),
     "onssen_mul_pack_f16": (c_int, [c_vp, c_vp, c_ll, c_int, c_vp, c_int, c_vp]),
     "onssen_pack_phase_input_f16": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_add_l2norm_pairs": (c_int, [c_vp, c_vp, c_ll, c_vp, c_vp]),
@@ -575,3 +579,41 @@ def add_inplace(a, b):
     _check(load().onssen_add_inplace(_p(_req(a, torch.float32)), _p(_req(b, torch.float32)), a.numel(), _stream()),
            "onssen_add_inplace")
     return a
+
+
+def relu_bwd(d_out, out):
+    lib = load()
+    B, T = out.shape[0], out.shape[1]
+    C = out.numel() // (B * T)
+    dz = torch.empty(T * B, C, device=out.device, dtype=torch.float32)
+    amax = torch.empty(1, device=out.device, dtype=torch.int32)
+    _check(lib.onssen_relu_bwd(_p(_req(d_out, torch.float32)), _p(_req(out, torch.float32)), B, T, C, _p(dz), _p(amax),
+                               _stream()), "onssen_sigmoid_bwd")
+    scale2 = torch.empty(2, device=out.device, dtype=torch.float32)
+    _check(lib.onssen_scale_from_amax_bits(_p(amax), 1024.0, _p(scale2), _stream()), "onssen_scale_from_amax_bits")
+    return dz, scale2
+
+
+def enhance_mid_bwd(d_est, pre, mask):
+    lib = load()
+    M, F = pre.shape
+    dz_pre, dz_mi = torch.empty_like(pre), torch.empty_like(pre)
+    amax = torch.empty(2, device=pre.device, dtype=torch.int32)
+    rc = lib.onssen_enhance_mid_bwd(_p(_req(d_est, torch.float32)), d_est.stride(0), _p(_req(pre, torch.float32)),
+                                    _p(_req(mask, torch.float32)), M, F, _p(dz_pre), _p(dz_mi), _p(amax), _stream())
+    _check(rc, "onssen_enhance_mid_bwd")
+    scs = []
+    for k in range(2):
+        sc = torch.empty(2, device=pre.device, dtype=torch.float32)
+        _check(lib.onssen_scale_from_amax_bits(_p(amax[k:]), 1024.0, _p(sc), _stream()), "onssen_scale_from_amax_bits")
+        scs.append(sc)
+    return dz_pre, scs[0], dz_mi, scs[1]
+
+
+def loss_mse_bwd(a, b, g):
+    lib = load()
+    d_a = torch.empty_like(a)
+    _check(lib.onssen_loss_mse_bwd(_p(_req(a, torch.float32)), _p(_req(b, torch.float32)), a.numel(),
+                                   _p(_req(g.float().reshape(1).contiguous(), torch.float32)), _p(d_a), _stream()),
+           "onssen_loss_mse_fwd")
+    return d_a

@@ -106,10 +106,12 @@ __global__ void colsum_final_kernel(const double* __restrict__ part, int nchunk,
 }
 
 // F.normalize backward + layout change: d_emb / emb are batch-first (B,T,F,D); dz is written time-major
-// [T*B][F*D] fp32:  dz = (de - e * <e,de>) * inv_norm.   One thread per (row, group).
+// [T*B][F*D] fp32:  dz = (de - e * <e,de>) * inv_norm.   One thread per (row, group); the group is read and
+// written as D/4 float4 (160 contiguous bytes per thread at D=40, neighbouring threads neighbouring groups).
+template <int D>
 __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const float* __restrict__ d_emb, const float* __restrict__ emb,
-                     const float* __restrict__ inv_norm, int B, int T, int F, int D, float* __restrict__ dz,
+                     const float* __restrict__ inv_norm, int B, int T, int F, float* __restrict__ dz,
                      unsigned int* __restrict__ amax_bits) {
   const long long total = (long long)B * T * F;
   float am = 0.f;
@@ -118,16 +120,27 @@ normalize_bwd_kernel(const float* __restrict__ d_emb, const float* __restrict__ 
     const int f = (int)(i % F);
     const long long bt = i / F;
     const int t = (int)(bt % T), b = (int)(bt / T);
-    const float* e = emb + i * D;
-    const float* g = d_emb + i * D;
+    const float4* e4 = reinterpret_cast<const float4*>(emb + i * D);
+    const float4* g4 = reinterpret_cast<const float4*>(d_emb + i * D);
+    float4 e[D / 4], g[D / 4];
     float dot = 0.f;
-    for (int k = 0; k < D; ++k) dot = fmaf(e[k], g[k], dot);
+#pragma unroll
+    for (int k = 0; k < D / 4; ++k) {
+      e[k] = e4[k];
+      g[k] = g4[k];
+      dot = fmaf(e[k].x, g[k].x, fmaf(e[k].y, g[k].y, fmaf(e[k].z, g[k].z, fmaf(e[k].w, g[k].w, dot))));
+    }
     const float inv = inv_norm[i];
-    float* o = dz + ((long long)t * B + b) * ((long long)F * D) + (long long)f * D;
-    for (int k = 0; k < D; ++k) {
-      const float v = (g[k] - e[k] * dot) * inv;
+    float4* o = reinterpret_cast<float4*>(dz + ((long long)t * B + b) * ((long long)F * D) + (long long)f * D);
+#pragma unroll
+    for (int k = 0; k < D / 4; ++k) {
+      float4 v;
+      v.x = (g[k].x - e[k].x * dot) * inv;
+      v.y = (g[k].y - e[k].y * dot) * inv;
+      v.z = (g[k].z - e[k].z * dot) * inv;
+      v.w = (g[k].w - e[k].w * dot) * inv;
       o[k] = v;
-      am = fmaxf(am, fabsf(v));
+      am = fmaxf(am, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
   }
   am = warp_max(am);
@@ -262,7 +275,7 @@ __global__ void pit_l1_bwd_kernel(const float* __restrict__ mask_a, const float*
 
 // sigmoid backward + layout change: d_out / out batch-first [B][T][C]; dz time-major [T*B][C]
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int B, int T, int C,
-                                   float* __restrict__ dz, unsigned int* __restrict__ amax_bits) {
+                                   int relu, float* __restrict__ dz, unsigned int* __restrict__ amax_bits) {
   const long long total = (long long)B * T * C;
   float am = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -271,12 +284,46 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ d_out, const float*
     const long long bt = i / C;
     const int t = (int)(bt % T), b = (int)(bt / T);
     const float o = out[i];
-    const float v = d_out[i] * o * (1.0f - o);
+    const float v = relu ? (o > 0.f ? d_out[i] : 0.f) : d_out[i] * o * (1.0f - o);
     dz[((long long)t * B + b) * C + c] = v;
     am = fmaxf(am, fabsf(v));
   }
   am = warp_max(am);
   if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_uint(am));
+}
+
+// middle of the enhancement model (enhancement.py:49-50), time-major [M][F]:  est = pre * mask, pre = relu(.),
+// mask = sigmoid(.):  dz_pre = d_est * mask * (pre > 0),  dz_mi = d_est * pre * mask * (1 - mask)
+__global__ void enhance_mid_bwd_kernel(const float* __restrict__ d_est, long long ld, const float* __restrict__ pre,
+                                       const float* __restrict__ mask, long long M, int F, float* __restrict__ dz_pre,
+                                       float* __restrict__ dz_mi, unsigned int* __restrict__ amax2) {
+  const long long total = M * F;
+  float a0 = 0.f, a1 = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / F;
+    const int f = (int)(i % F);
+    const float g = d_est[m * ld + f], pv = pre[i], mk = mask[i];
+    const float v0 = pv > 0.f ? g * mk : 0.f;
+    const float v1 = g * pv * mk * (1.0f - mk);
+    dz_pre[i] = v0;
+    dz_mi[i] = v1;
+    a0 = fmaxf(a0, fabsf(v0));
+    a1 = fmaxf(a1, fabsf(v1));
+  }
+  a0 = warp_max(a0); a1 = warp_max(a1);
+  if ((threadIdx.x & 31) == 0) {
+    if (a0 > 0.f) atomicMax(amax2, __float_as_uint(a0));
+    if (a1 > 0.f) atomicMax(amax2 + 1, __float_as_uint(a1));
+  }
+}
+
+// nn.MSELoss backward: d_a = 2 (a - b) / n * g[0]
+__global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                               const float* __restrict__ g, float* __restrict__ d_a) {
+  const float k = 2.0f / (float)n * g[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d_a[i] = (a[i] - b[i]) * k;
 }
 
 __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
@@ -300,13 +347,37 @@ extern "C" int onssen_loss_pit_l1_bwd(const float* mask_a, const float* mask_b, 
   return ONSSEN_CHECK_LAUNCH();
 }
 
-extern "C" int onssen_sigmoid_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz,
-                                  void* amax_bits_u32, void* stream) {
+static int act_bwd(const float* d_out, const float* out, int B, int T, int C, int relu, float* dz,
+                   void* amax_bits_u32, void* stream) {
   if (!d_out || !out || !dz || !amax_bits_u32) return ONSSEN_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(amax_bits_u32, 0, 4, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
-  sigmoid_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, s>>>(d_out, out, B, T, C, dz,
+  sigmoid_bwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, s>>>(d_out, out, B, T, C, relu, dz,
                                                                         (unsigned int*)amax_bits_u32);
+  return ONSSEN_CHECK_LAUNCH();
+}
+extern "C" int onssen_sigmoid_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz,
+                                  void* amax_bits_u32, void* stream) {
+  return act_bwd(d_out, out, B, T, C, 0, dz, amax_bits_u32, stream);
+}
+extern "C" int onssen_relu_bwd(const float* d_out, const float* out, int B, int T, int C, float* dz,
+                               void* amax_bits_u32, void* stream) {
+  return act_bwd(d_out, out, B, T, C, 1, dz, amax_bits_u32, stream);
+}
+extern "C" int onssen_enhance_mid_bwd(const float* d_est, long long ld, const float* pre, const float* mask,
+                                      long long M, int F, float* dz_pre, float* dz_mi, void* amax_bits_2xu32,
+                                      void* stream) {
+  if (!d_est || !pre || !mask || !dz_pre || !dz_mi || !amax_bits_2xu32 || M <= 0 || F <= 0) return ONSSEN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(amax_bits_2xu32, 0, 8, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+  enhance_mid_bwd_kernel<<<grid_for(M * F, 256), 256, 0, s>>>(d_est, ld, pre, mask, M, F, dz_pre, dz_mi,
+                                                             (unsigned int*)amax_bits_2xu32);
+  return ONSSEN_CHECK_LAUNCH();
+}
+extern "C" int onssen_loss_mse_bwd(const float* a, const float* b, long long n, const float* g, float* d_a,
+                                   void* stream) {
+  if (!a || !b || !g || !d_a || n <= 0) return ONSSEN_ERR_ARG;
+  mse_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, g, d_a);
   return ONSSEN_CHECK_LAUNCH();
 }
 
@@ -372,8 +443,15 @@ extern "C" int onssen_normalize_bwd(const float* d_emb, const float* emb, const 
   if (!d_emb || !emb || !inv_norm || !dz || !amax_bits_u32) return ONSSEN_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(amax_bits_u32, 0, 4, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
-  normalize_bwd_kernel<<<grid_for((long long)B * T * F, 256), 256, 0, s>>>(d_emb, emb, inv_norm, B, T, F, D, dz,
-                                                                           (unsigned int*)amax_bits_u32);
+  if ((D & 3) || ((uintptr_t)d_emb & 15) || ((uintptr_t)emb & 15) || ((uintptr_t)dz & 15)) return ONSSEN_ERR_UNSUPPORTED;
+  const int grid = grid_for((long long)B * T * F, 256);
+#define ONSSEN_NB(DD) \
+  case DD: normalize_bwd_kernel<DD><<<grid, 256, 0, s>>>(d_emb, emb, inv_norm, B, T, F, dz, (unsigned int*)amax_bits_u32); break;
+  switch (D) {
+    ONSSEN_NB(4) ONSSEN_NB(8) ONSSEN_NB(12) ONSSEN_NB(16) ONSSEN_NB(20) ONSSEN_NB(24) ONSSEN_NB(32) ONSSEN_NB(40)
+    default: return ONSSEN_ERR_UNSUPPORTED;
+  }
+#undef ONSSEN_NB
   return ONSSEN_CHECK_LAUNCH();
 }
 

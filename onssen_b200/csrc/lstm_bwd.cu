@@ -35,6 +35,8 @@ __device__ __forceinline__ float hash_uniform32(unsigned int seed_lo, unsigned i
   return (float)(x >> 8) * (1.0f / 16777216.0f);
 }
 
+int g_bwd_persistent = 1;   // 0: one launch per step (validation path), see onssen_blstm_rec_bwd_set_persistent
+
 __device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, const uint32_t* b) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -164,6 +166,184 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const BwdParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant: ONE cooperative launch per layer.  CTA (unit block, dir, batch block) keeps its W_hh^T
+// fragments in shared memory for all T steps; the per-step exchange of dG between the CTAs of a direction uses
+// the forward kernel's flag-bit protocol: the caller picks the loss scale so that |dG * scale| < 2, which leaves
+// bit 14 of every fp16 free as a step-parity flag -> self-validating data, no fences, no grid barrier.
+__device__ __forceinline__ uint2 ld_relaxed_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(void* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ __half to_half_flag_range(float x) {   // clamp to the largest fp16 below 2.0
+  x = fminf(fmaxf(x, -1.9990234375f), 1.9990234375f);
+  return __float2half_rn(x);
+}
+
+__global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdParams p) {
+  extern __shared__ __align__(16) uint8_t bsm[];
+  const int Hp = p.Hp, B = p.B, T = p.T;
+  const int G4 = 4 * Hp;
+  const int ksteps = G4 / 16;
+  uint4* a_s = reinterpret_cast<uint4*>(bsm);                                   // [ksteps][2][32] uint4
+  float (*red)[32][33] = reinterpret_cast<float (*)[32][33]>(bsm + (size_t)ksteps * 2 * 32 * 16);
+  const int ub = blockIdx.x, dir = blockIdx.y, bb = blockIdx.z;
+  const int nub = Hp / 32, nbb = gridDim.z;
+  const int b0 = bb * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const float inv_scale = p.scale2[1], scale = p.scale2[0];
+  const float keep_scale = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  // resident W_hh^T fragments
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wt) + ((size_t)(dir * nub + ub) * ksteps) * 2 * 32;
+    for (int i = tid; i < ksteps * 64; i += 256) a_s[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int per_warp = (ksteps + 7) / 8;
+  const int ks_begin = warp * per_warp;
+  const int ks_end = min(ksteps, ks_begin + per_warp);
+  const size_t frag_group = (size_t)ksteps * 4 * 32;   // uint2 per (parity, dir, bb)
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? T - 1 - s : s;
+    const int t_fp = dir == 0 ? t - 1 : t + 1;
+    // ---- per-step inputs that do not depend on the recurrence: issue their loads before the exchange wait
+    float4 a4[4];
+    float ct[4], cprev[4], dyv[4];
+    long long oyv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int ul = idx & 31, bl = idx >> 5;
+      const int b = min(b0 + bl, B - 1);               // clamped: results of pad columns are replaced by zeros
+      const int u = ub * 32 + ul;
+      const long long m = (long long)t * B + b;
+      oyv[i] = m * (2 * Hp) + dir * Hp + u;
+      a4[i] = *reinterpret_cast<const float4*>(p.actg + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul);
+      ct[i] = p.c[oyv[i]];
+      cprev[i] = (t_fp >= 0 && t_fp < T) ? p.c[((long long)t_fp * B + b) * (2 * Hp) + dir * Hp + u] : 0.f;
+      dyv[i] = p.dy[oyv[i]];
+    }
+    // ---- phase A: dh_rec = W_hh^T slice x dG_{previous step} (all gate rows of this direction)
+    if (s > 0) {
+      float acc[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+      const unsigned int fbit = ((((unsigned int)(s - 1)) >> 1) & 1u) ^ 1u;
+      const unsigned int fw = fbit ? 0x40004000u : 0u;
+      const uint2* bfr = reinterpret_cast<const uint2*>(p.frag) +
+                         (((size_t)((s - 1) & 1) * 2 + dir) * nbb + bb) * frag_group + lane;
+      constexpr int U = 4;
+      for (int ksb = ks_begin; ksb < ks_end; ksb += U) {
+        uint2 bf[U][4];
+        unsigned int pending = 0;
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu)
+          if (ksb + uu < ks_end) pending |= 0xFu << (4 * uu);
+        while (pending) {
+#pragma unroll
+          for (int uu = 0; uu < U; ++uu)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              if (pending & (1u << (4 * uu + nt))) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * 4 + nt) * 32);
+#pragma unroll
+          for (int uu = 0; uu < U; ++uu)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              if ((pending & (1u << (4 * uu + nt))) && (bf[uu][nt].x & 0x40004000u) == fw &&
+                  (bf[uu][nt].y & 0x40004000u) == fw) {
+                bf[uu][nt].x &= ~0x40004000u;
+                bf[uu][nt].y &= ~0x40004000u;
+                pending &= ~(1u << (4 * uu + nt));
+              }
+        }
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+          if (ksb + uu < ks_end) {
+            const uint4 a0 = a_s[((size_t)(ksb + uu) * 2 + 0) * 32 + lane];
+            const uint4 a1 = a_s[((size_t)(ksb + uu) * 2 + 1) * 32 + lane];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              mma_16816(acc[0][nt], reinterpret_cast<const uint32_t*>(&a0), reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
+              mma_16816(acc[1][nt], reinterpret_cast<const uint32_t*>(&a1), reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          red[warp][mt * 16 + g][nt * 8 + 2 * tq] = acc[mt][nt][0];
+          red[warp][mt * 16 + g][nt * 8 + 2 * tq + 1] = acc[mt][nt][1];
+          red[warp][mt * 16 + g + 8][nt * 8 + 2 * tq] = acc[mt][nt][2];
+          red[warp][mt * 16 + g + 8][nt * 8 + 2 * tq + 1] = acc[mt][nt][3];
+        }
+    }
+    __syncthreads();
+    // ---- phase B: gate derivatives of this CTA's units at step t; publish dG in B-fragment order
+    const unsigned int fbit_w = ((((unsigned int)s) >> 1) & 1u) ^ 1u;
+    const unsigned int fww = fbit_w ? 0x40004000u : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int ul = idx & 31, bl = idx >> 5;
+      const bool valid = (b0 + bl) < B;
+      const int u = ub * 32 + ul;
+      float dh_rec = 0.f;
+      if (s > 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) dh_rec += red[w][ul][bl];
+        dh_rec *= inv_scale;
+      }
+      float dy = dyv[i];
+      if (p.dropout_p > 0.f) {
+        const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)oyv[i]);
+        dy = rnd < p.dropout_p ? 0.f : dy * keep_scale;
+      }
+      const float dh = dy + dh_rec;
+      const float tc = tanhf(ct[i]);
+      float* dcp = p.dc + ((size_t)dir * B + min(b0 + bl, B - 1)) * Hp + u;
+      const float dct = dh * a4[i].w * (1.0f - tc * tc) + ((s > 0 && valid) ? *dcp : 0.f);
+      float4 d4;
+      d4.x = dct * a4[i].z * a4[i].x * (1.0f - a4[i].x);
+      d4.y = dct * cprev[i] * a4[i].y * (1.0f - a4[i].y);
+      d4.z = dct * a4[i].x * (1.0f - a4[i].z * a4[i].z);
+      d4.w = dh * tc * a4[i].w * (1.0f - a4[i].w);
+      uint2 o = make_uint2(0u, 0u);
+      if (valid) {
+        *dcp = dct * a4[i].y;
+        const long long m = (long long)t * B + b0 + bl;
+        *reinterpret_cast<float4*>(p.actg + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul) = d4;
+        __half2 lo = __halves2half2(to_half_flag_range(d4.x * scale), to_half_flag_range(d4.y * scale));
+        __half2 hi = __halves2half2(to_half_flag_range(d4.z * scale), to_half_flag_range(d4.w * scale));
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p.dg16 + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul) = o;
+      }
+      if (s + 1 < T) {   // pad batch columns publish zeros so that every fragment entry becomes fresh
+        const int ks = ub * 8 + (ul >> 2);
+        const int j = ul & 3;
+        const int reg = j >> 1;
+        const int tq0 = (j & 1) * 2;
+        uint32_t* fb = p.frag + ((((size_t)(s & 1) * 2 + dir) * nbb + bb) * frag_group + ((size_t)ks * 4 + (bl >> 3)) * 32) * 2;
+        st_relaxed_u32(fb + ((bl & 7) * 4 + tq0) * 2 + reg, o.x | fww);
+        st_relaxed_u32(fb + ((bl & 7) * 4 + tq0 + 1) * 2 + reg, o.y | fww);
+      }
+    }
+    __syncthreads();   // red[] is rewritten by the next step's phase A
+  }
+}
+
 // W_hh [4H][H] fp32 (both directions) -> W_hh^T in mma.m16n8k16 A-fragment order (fp16):
 // [dir][ub][kstep][mtile][lane][word w][2 halves];  word w covers row = mtile*16 + lane/4 + 8*(w&1) (hidden unit
 // ub*32 + row) and k = 16*kstep + 2*(lane%4) + 8*(w>>1) + {0,1} (permuted gate row index)
@@ -205,6 +385,8 @@ extern "C" int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, 
   return ONSSEN_CHECK_LAUNCH();
 }
 
+extern "C" void onssen_blstm_rec_bwd_set_persistent(int on) { g_bwd_persistent = on ? 1 : 0; }
+
 extern "C" size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H) {
   const int Hp = hp_of(H);
   // dc carry [2][B][Hp] fp32 + fragment exchange [2 parity][2 dir][nbb][4Hp/16][4][32][2] u32
@@ -228,6 +410,25 @@ extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch, 0, onssen_blstm_rec_bwd_scratch_bytes(B, H), s) != cudaSuccess) return ONSSEN_ERR_CUDA;
   dim3 grid(p.Hp / 32, 2, (B + 31) / 32);
+  // persistent path: W_hh^T fragments resident in smem, one cooperative launch for all T steps
+  {
+    const size_t smem = (size_t)(4 * p.Hp / 16) * 2 * 32 * 16 + (size_t)8 * 32 * 33 * sizeof(float);
+    const int nblocks = (int)(grid.x * grid.y * grid.z);
+    if (g_bwd_persistent && smem <= 225 * 1024 && nblocks <= num_sms()) {
+      if (cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess)
+        return ONSSEN_ERR_CUDA;
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persistent_kernel, 256, smem) == cudaSuccess &&
+          per_sm * num_sms() >= nblocks) {
+        void* args[] = {(void*)&p};
+        if (cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_kernel, grid, dim3(256), args, smem, s) !=
+            cudaSuccess)
+          return ONSSEN_ERR_CUDA;
+        return ONSSEN_OK;
+      }
+    }
+  }
   for (int step = 0; step < T; ++step) {
     p.s = step;
     lstm_bwd_step_kernel<<<grid, 256, 0, s>>>(p);

@@ -40,20 +40,24 @@ def blstm_forward_train(rnn, cache, x, training, last_f32):
     return layers, packed, (y_f if last_f32 else y_h)
 
 
-def linear_backward(dz32, sc, a_in_h, w_p, N, H, grads, name):
-    """Linear(2H -> N) on the padded BLSTM-output layout: dz32 [M][N] fp32 (time-major), sc = scale2 of dz32,
-    a_in_h fp16 [M][2Hp] the layer's input, w_p fp16 [N][2Hp]. Fills grads[name.weight/bias]; returns dA [M][2Hp]."""
+def linear_backward(dz32, sc, a_in_h, w_p, N, H, grads, name, K=None, want_dA=True):
+    """Linear on packed operands: dz32 [M][N] fp32 (time-major), sc = scale2 of dz32, a_in_h fp16 [M][Kp] the layer's
+    input, w_p fp16 [N][Kp].  K is None: the input is a BLSTM output in the padded layout (K = 2H, Kp = 2Hp); else a
+    plain K-feature input padded to Kp.  Fills grads[name.weight/bias]; returns dA [M][Kp] (or None)."""
     M = dz32.shape[0]
-    Hp, Mp = _lib.hp_of(H), _lib.pad64(M)
-    dz_n, dz_t = _lib.cast_transpose_f16(dz32, sc)
+    Kp, Mp = a_in_h.shape[1], _lib.pad64(M)
+    dz_n, dz_t = _lib.cast_transpose_f16(dz32, sc, want_n=want_dA)
     grads[name + ".bias"] = _lib.colsum(dz32)
-    aT = _lib.transpose_shift_f16(a_in_h, 0, 2 * Hp)
-    dWp = torch.empty(N, 2 * Hp, device=dz32.device, dtype=torch.float32)
-    _lib.gemm_f16_ex(dz_t, aT, None, dWp, N, 2 * Hp, Mp, 2 * Hp, out_scale=sc[1:])
-    grads[name + ".weight"] = _lib.unpack_linear_grad(dWp, N, 2 * H, True, H)
-    wT = _lib.transpose_shift_f16(w_p, 0, 2 * Hp)
-    dA = torch.empty(M, 2 * Hp, device=dz32.device, dtype=torch.float32)
-    _lib.gemm_f16_ex(dz_n, wT, None, dA, M, 2 * Hp, dz_n.shape[1], 2 * Hp, out_scale=sc[1:])
+    aT = _lib.transpose_shift_f16(a_in_h, 0, Kp)
+    dWp = torch.empty(N, Kp, device=dz32.device, dtype=torch.float32)
+    _lib.gemm_f16_ex(dz_t, aT, None, dWp, N, Kp, Mp, Kp, out_scale=sc[1:])
+    grads[name + ".weight"] = (_lib.unpack_linear_grad(dWp, N, 2 * H, True, H) if K is None
+                               else _lib.unpack_linear_grad(dWp, N, K, False, 0))
+    if not want_dA:
+        return None
+    wT = _lib.transpose_shift_f16(w_p, 0, Kp)
+    dA = torch.empty(M, Kp, device=dz32.device, dtype=torch.float32)
+    _lib.gemm_f16_ex(dz_n, wT, None, dA, M, Kp, dz_n.shape[1], Kp, out_scale=sc[1:])
     return dA
 
 
@@ -67,7 +71,9 @@ def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None):
         lay = layers[l]
         wih_p = packed[l][0]
         (wf, wr) = lstm_layer_params(rnn, l)
-        sc = _lib.amax_scale(dY)
+        # scale so that amax(dY)*scale = 2^-4: |dG*scale| stays below 2 (bit 14 of the fp16 exchange words is the
+        # step-parity flag of the persistent BPTT kernel) with 32x headroom for the cell-gradient accumulation
+        sc = _lib.amax_scale(dY, target=0.0625)
         dg16 = torch.empty(M, 8 * Hp, device=dev, dtype=torch.float16)
         whh_t = _lib.lstm_pack_whh_t(wf[1], wr[1], H)
         _lib.blstm_rec_bwd(lay["gates"], dg16, lay["c"], dY, whh_t, sc, B, T, H, lay["p"], lay["seed"], l)
@@ -106,6 +112,7 @@ class _ModelFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, fwd, bwd, x, *params):
+        # x is a tensor, or a tuple of tensors for models with several inputs (none of them needs a gradient)
         outs, saved = fwd(model, x)
         ctx.model, ctx.saved, ctx.bwd = model, saved, bwd
         ctx.names = [n for n, _ in model.named_parameters()]
@@ -211,6 +218,54 @@ def chimera_backward(model, saved, d_outs, on_grads=None):
         grads["fc_mi.bias"] = torch.zeros_like(model.fc_mi.bias)
     if dY is None:
         dY = torch.zeros(M, 2 * _lib.hp_of(H), device=dev, dtype=torch.float32)
+    if on_grads is not None:
+        on_grads(dict(grads))
+    return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)
+
+
+# ------------------------------------------------------------------------------------------------ enhance
+def enhance_forward_train(model, x_and_noisy):
+    x, mag_noisy = x_and_noisy
+    rnn, bn = model.rnn, model.bn
+    B, T, F = x.shape
+    H = rnn.hidden_size
+    M = T * B
+    dev = x.device
+    layers, packed, y_f = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=True)
+    a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True)
+    bn.num_batches_tracked += 1
+    w_mi = model._mi.get([model.fc_mi.weight], lambda: _lib.pack_linear_f16(model.fc_mi.weight, True, H))
+    w_pre = model._pre.get([model.fc_pre.weight], lambda: _lib.pack_linear_f16(model.fc_pre.weight, False))
+    w_post = model._post.get([model.fc_post.weight], lambda: _lib.pack_linear_f16(model.fc_post.weight, False))
+    mask = torch.empty(M, F, device=dev, dtype=torch.float32)
+    _lib.gemm_f16(a_h, w_mi, model.fc_mi.bias.detach(), mask, M, F, a_h.shape[1], F, epi=1)
+    noisy_h = _lib.pack_input_f16(mag_noisy.float().contiguous())
+    pre = torch.empty(M, F, device=dev, dtype=torch.float32)
+    _lib.gemm_f16(noisy_h, w_pre, model.fc_pre.bias.detach(), pre, M, F, noisy_h.shape[1], F, epi=2)
+    est_h = _lib.mul_pack_f16(pre, mask)
+    clean = torch.empty(B, T, F, device=dev, dtype=torch.float32)
+    _lib.gemm_f16(est_h, w_post, model.fc_post.bias.detach(), clean, M, F, est_h.shape[1], F, epi=2, remap_inner=B,
+                  remap_outer=T)
+    saved = dict(layers=layers, packed=packed, y_f=y_f, a_h=a_h, mean=mean, invstd=invstd, mask=mask, pre=pre,
+                 noisy_h=noisy_h, est_h=est_h, clean=clean, w_mi=w_mi, w_pre=w_pre, w_post=w_post, shape=(B, T, F))
+    return clean, saved
+
+
+def enhance_backward(model, saved, d_outs, on_grads=None):
+    d_clean, = d_outs
+    rnn, bn = model.rnn, model.bn
+    B, T, F = saved["shape"]
+    H = rnn.hidden_size
+    M = T * B
+    grads = {}
+    dzpost, sc = _lib.relu_bwd(d_clean, saved["clean"])
+    d_est = linear_backward(dzpost, sc, saved["est_h"], saved["w_post"], F, H, grads, "fc_post", K=F)
+    dz_pre, sc_pre, dz_mi, sc_mi = _lib.enhance_mid_bwd(d_est, saved["pre"], saved["mask"])
+    linear_backward(dz_pre, sc_pre, saved["noisy_h"], saved["w_pre"], F, H, grads, "fc_pre", K=F, want_dA=False)
+    dA = linear_backward(dz_mi, sc_mi, saved["a_h"], saved["w_mi"], F, H, grads, "fc_mi")
+    dY, grads["bn.weight"], grads["bn.bias"] = _lib.bn_backward(dA, saved["y_f"], M, H, bn.weight.detach(),
+                                                                saved["mean"], saved["invstd"])
     if on_grads is not None:
         on_grads(dict(grads))
     return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)

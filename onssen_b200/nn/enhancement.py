@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward, require_no_grad
+from ._blstm import PackCache, blstm_forward
 
 
 class enhance(nn.Module):
@@ -26,7 +26,12 @@ class enhance(nn.Module):
         assert len(input) == 2, "There must be two tensors in the input for the enhance network"
         x, mag_noisy = input
         x = x.float()
-        require_no_grad("enhance", x, self.fc_mi.weight)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if not self.training:
+                raise NotImplementedError("enhance: gradients are implemented for train() mode (batch-statistics "
+                                          "BatchNorm), call model.train()")
+            from ._train import enhance_backward, enhance_forward_train, run_model
+            return [run_model(self, enhance_forward_train, enhance_backward, (x, mag_noisy))]
         B, T, F = x.shape
         H = self.hidden_dim
         M = T * B

@@ -123,6 +123,14 @@ def main():
             clean_train, = en([tt(feat), tt(mix)])
             l_msa = onssen.loss.loss_mask_msa([clean_eval], [tt(mag1), tt(cos1)])
             l_psa = onssen.loss.loss_mask_psa([torch.sigmoid(clean_eval)], [tt(mix), tt(mag1), tt(cos1)])
+        # gradients of loss_mask_msa (scalar MSE) in train mode
+        en.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()}, strict=False)
+        en.train()
+        en.zero_grad()
+        cl_g, = en([tt(feat), tt(mix)])
+        onssen.loss.loss_mask_msa([cl_g], [tt(mag1), tt(cos1)]).backward()
+        np.savez_compressed(os.path.join(out_dir, f"enhancegrad_{name}.npz"),
+                            **{"g:" + k: v.grad.detach().numpy().copy() for k, v in en.named_parameters()})
         np.savez_compressed(os.path.join(out_dir, f"enhance_{name}.npz"), cfg=np.array([B, T, F, H, L, D]), feature=feat,
                             mag_noisy=mix, mag_clean=mag1, cos_diff=cos1, clean_eval=clean_eval.numpy(),
                             clean_train=clean_train.numpy(), loss_msa=l_msa.numpy(), loss_psa=l_psa.numpy(),

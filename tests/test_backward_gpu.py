@@ -88,3 +88,22 @@ def test_chimera_gradients_vs_reference(cuda_device, name):
         worst = max(worst, e)
         assert e < 3e-2, (k, e)
     print("chimera++ worst relative gradient error", worst)
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_enhance_gradients_vs_reference(cuda_device, name):
+    import onssen_b200 as ob
+    p, g = load_golden(f"enhance_{name}.npz")
+    gz = np.load(f"tests/golden/enhancegrad_{name}.npz")
+    B, T, F, H, L, D = [int(v) for v in g["cfg"]]
+    model = ob.nn.enhance(F, H, L, dropout=0.0).to(cuda_device).train()
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()}, strict=False)
+    cu = lambda a: torch.from_numpy(a).to(cuda_device)
+    clean, = model([cu(g["feature"]), cu(g["mag_noisy"])])
+    ob.loss.loss_mask_msa([clean], [cu(g["mag_clean"]), cu(g["cos_diff"])]).backward()
+    worst = 0.0
+    for k, v in model.named_parameters():
+        e = rel_err(v.grad.cpu().numpy(), gz["g:" + k])
+        worst = max(worst, e)
+        assert e < 3e-2, (k, e)
+    print("enhance worst relative gradient error", worst)

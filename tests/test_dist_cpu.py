@@ -101,3 +101,25 @@ def test_loader_file_sharding(tmp_path):
     (mix, s1, s2), lengths = full._load(full.file_list[:2])
     assert mix.shape == (2, 4100) and lengths.tolist() == [4000, 4100]
     assert float(mix[0, 4000:].abs().max()) == 0.0           # zero padded to the batch pitch
+
+
+def test_edinburgh_loader_file_conventions(tmp_path):
+    from scipy.io import wavfile
+    from onssen_b200.data import edinburgh_tts_dataloader
+    for sub in ("noisy_trainset_28spk_wav", "clean_trainset_28spk_wav"):
+        (tmp_path / sub).mkdir()
+    rng = np.random.RandomState(1)
+    names = [f"p{i}.wav" for i in range(3)]
+    for i, n in enumerate(names):
+        clean = (rng.standard_normal(3000 + 10 * i) * 2000).astype(np.int16)
+        noise = (rng.standard_normal(3000 + 10 * i) * 500).astype(np.int16)
+        wavfile.write(str(tmp_path / "clean_trainset_28spk_wav" / n), 16000, clean)
+        wavfile.write(str(tmp_path / "noisy_trainset_28spk_wav" / n), 16000, (clean + noise).astype(np.int16))
+    (tmp_path / "train").write_text("\n".join(names) + "\n")
+    fo = dict(data_path=str(tmp_path), batch_size=2, frame_length=20, sampling_rate=16000, window_size=512, hop_size=128,
+              db_threshold=40)
+    ld = edinburgh_tts_dataloader("chimera++", fo, "train")
+    assert len(ld.file_list) == 3 and len(ld) == 2
+    (mix, clean, noise), lengths = ld._load(sorted(ld.file_list)[:2])
+    assert mix.shape == (2, 3010) and lengths.tolist() == [3000, 3010]
+    assert torch.allclose(mix - clean, noise, atol=1e-6)       # "speaker 2" = mix - clean
