@@ -246,6 +246,9 @@ size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H);
  * the scale passed to onssen_blstm_rec_bwd to keep |dG*scale| < 2, i.e. scale2 from a target <= 2^-4 * headroom);
  * 0: one launch per time step (validation path). */
 void onssen_blstm_rec_bwd_set_persistent(int on);
+/* debug: clock64 stamps of CTA 0 of the persistent BPTT kernel, steps 100..107, [step][slot 0..7][warp 0..7]
+   (512 int64); NULL = off */
+void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64);
 int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
                          void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
                          unsigned long long seed, unsigned long long offset, void* stream);
@@ -300,6 +303,25 @@ int onssen_loss_mse_fwd(const float* a, const float* b, long long n, float* out,
 int onssen_loss_phase_cos_fwd(const float* phase_a, const float* phase_b, const float* phase_s1,
                               const float* phase_s2, const float* mag_mix, const int32_t* perm, int B, int N,
                               float* out, void* stream);
+
+/* ---- phase network training (REPAIRED restatement; no reference oracle) ----------------
+ * loss_phase.py:26-35 backward: gradient of -sum mag*cos_sim w.r.t. the two phase estimates under `perm`;
+ * g = upstream gradient per utterance [B]. */
+int onssen_loss_phase_cos_bwd(const float* phase_a, const float* phase_b, const float* phase_s1, const float* phase_s2,
+                              const float* mag_mix, const int32_t* perm, const float* g, int B, int N,
+                              float* d_phase_a, float* d_phase_b, void* stream);
+/* phase_network.py:55-56,63-64 backward: y = normalize(x + residual) over (re,im); d_y/x/residual [B][T][F][2];
+ * dz = d loss / d x, time-major [T*B][2F]; amax_bits_u32 receives max|dz| as float bits. */
+int onssen_l2norm_pairs_bwd(const float* d_y, const float* x, const float* residual, int B, int T, int F, float* dz,
+                            void* amax_bits_u32, void* stream);
+/* phase_network.py:47-49 backward: d_masks[b][t][f][s_idx] += d_xin[t*B+b][f] * x_mag[b][t][f]
+ * (d_xin = gradient of the second BLSTM's packed input, row stride ld). */
+int onssen_phase_input_bwd(const float* d_xin, long long ld, const float* x_mag, int B, int T, int F, int S, int s_idx,
+                           float* d_masks, void* stream);
+
+/* loss_mask.py:25-40 backward: d_mask = g[b] * sign(mask*noisy - min(noisy, relu(clean*cos))) * noisy. */
+int onssen_loss_l1_psa_bwd(const float* mask, const float* mag_noisy, const float* mag_clean, const float* cos_diff,
+                           const float* g, int B, int N, float* d_mask, void* stream);
 
 #ifdef __cplusplus
 }

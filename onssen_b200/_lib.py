@@ -64,6 +64,11 @@ _SIGNATURES = {
                                            c_vp, c_sz, c_vp]),
     "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_bwd_set_persistent": (None, [c_int]),
+    "onssen_blstm_rec_bwd_set_trace": (None, [c_vp]),
+    "onssen_loss_l1_psa_bwd": (c_int, [c_vp] * 5 + [c_int] * 2 + [c_vp] * 2),
+    "onssen_loss_phase_cos_bwd": (c_int, [c_vp] * 7 + [c_int] * 2 + [c_vp] * 3),
+    "onssen_l2norm_pairs_bwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_vp] * 3),
+    "onssen_phase_input_bwd": (c_int, [c_vp, c_ll, c_vp] + [c_int] * 5 + [c_vp] * 2),
     "onssen_blstm_rec_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
     "onssen_loss_pit_l1_bwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_vp]),
     "onssen_sigmoid_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
@@ -617,3 +622,49 @@ def loss_mse_bwd(a, b, g):
                                    _p(_req(g.float().reshape(1).contiguous(), torch.float32)), _p(d_a), _stream()),
            "onssen_loss_mse_fwd")
     return d_a
+
+
+def loss_phase_cos_bwd(pa, pb, s1, s2, mag, perm, g):
+    lib = load()
+    B = mag.shape[0]
+    N = mag.numel() // B
+    d_pa, d_pb = torch.empty_like(pa), torch.empty_like(pb)
+    rc = lib.onssen_loss_phase_cos_bwd(*[_p(_req(t, torch.float32)) for t in (pa, pb, s1, s2, mag)],
+                                       _p(_req(perm, torch.int32)), _p(_req(g.float().contiguous(), torch.float32)), B, N,
+                                       _p(d_pa), _p(d_pb), _stream())
+    _check(rc, "onssen_loss_phase_cos_bwd")
+    return d_pa, d_pb
+
+
+def l2norm_pairs_bwd(d_y, x, residual):
+    """-> (dz fp32 [T*B][2F] time-major, scale2)"""
+    lib = load()
+    B, T, F, _ = x.shape
+    dz = torch.empty(T * B, 2 * F, device=x.device, dtype=torch.float32)
+    amax = torch.empty(1, device=x.device, dtype=torch.int32)
+    _check(lib.onssen_l2norm_pairs_bwd(_p(_req(d_y, torch.float32)), _p(_req(x, torch.float32)),
+                                       _p(_req(residual, torch.float32)), B, T, F, _p(dz), _p(amax), _stream()),
+           "onssen_l2norm_pairs_bwd")
+    scale2 = torch.empty(2, device=x.device, dtype=torch.float32)
+    _check(lib.onssen_scale_from_amax_bits(_p(amax), 1024.0, _p(scale2), _stream()), "onssen_scale_from_amax_bits")
+    return dz, scale2
+
+
+def phase_input_bwd(d_xin, x_mag, d_masks, s_idx):
+    lib = load()
+    B, T, F = x_mag.shape
+    S = d_masks.shape[-1]
+    _check(lib.onssen_phase_input_bwd(_p(_req(d_xin, torch.float32)), d_xin.stride(0), _p(_req(x_mag, torch.float32)), B, T,
+                                      F, S, s_idx, _p(_req(d_masks, torch.float32)), _stream()), "onssen_phase_input_bwd")
+    return d_masks
+
+
+def loss_l1_psa_bwd(mask, noisy, clean, cosd, g):
+    lib = load()
+    B = noisy.shape[0]
+    d_mask = torch.empty_like(mask)
+    rc = lib.onssen_loss_l1_psa_bwd(*[_p(_req(t, torch.float32)) for t in (mask, noisy, clean, cosd)],
+                                    _p(_req(g.float().contiguous(), torch.float32)), B, noisy.numel() // B, _p(d_mask),
+                                    _stream())
+    _check(rc, "onssen_loss_l1_psa_bwd")
+    return d_mask

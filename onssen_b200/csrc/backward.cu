@@ -292,6 +292,97 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ d_out, const float*
   if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_uint(am));
 }
 
+// ---- phase network (repaired phase_network.py:54-64 / loss_phase.py:26-35) ---------------------------------
+// d/d(est) of  -sum_n mag * (cos(X,s1) + cos(Y,s2)),  (X,Y) = (A,B) if perm==0 else (B,A);  cos with
+// F.cosine_similarity's eps clamp on each norm;  g = upstream gradient per utterance
+__global__ void phase_cos_bwd_kernel(const float* __restrict__ pa, const float* __restrict__ pb,
+                                     const float* __restrict__ s1, const float* __restrict__ s2,
+                                     const float* __restrict__ mag, const int32_t* __restrict__ perm,
+                                     const float* __restrict__ g, int B, int N, float* __restrict__ d_pa,
+                                     float* __restrict__ d_pb) {
+  const long long total = (long long)B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / N);
+    const bool swap = perm[b] != 0;
+    const float w = -mag[i] * g[b];
+    auto grad = [&](float2 x, float2 y) {   // d cos(x,y) / dx
+      const float rx = sqrtf(x.x * x.x + x.y * x.y), ry = sqrtf(y.x * y.x + y.y * y.y);
+      const float nx = fmaxf(rx, 1e-8f), ny = fmaxf(ry, 1e-8f);
+      const float inv = 1.0f / (nx * ny);
+      float2 d = make_float2(y.x * inv, y.y * inv);
+      if (rx > 1e-8f) {                     // the clamp is inactive: the norm depends on x
+        const float c = (x.x * y.x + x.y * y.y) * inv / (nx * nx);
+        d.x -= c * x.x;
+        d.y -= c * x.y;
+      }
+      return d;
+    };
+    const float2 A = reinterpret_cast<const float2*>(pa)[i], Bv = reinterpret_cast<const float2*>(pb)[i];
+    const float2 S1 = reinterpret_cast<const float2*>(s1)[i], S2 = reinterpret_cast<const float2*>(s2)[i];
+    const float2 da = grad(A, swap ? S2 : S1), db = grad(Bv, swap ? S1 : S2);
+    reinterpret_cast<float2*>(d_pa)[i] = make_float2(w * da.x, w * da.y);
+    reinterpret_cast<float2*>(d_pb)[i] = make_float2(w * db.x, w * db.y);
+  }
+}
+
+// y = v / max(|v|, 1e-12), v = ph + x_phase over (re, im) pairs; d_y / ph / x_phase batch-first [B][T][F][2];
+// dz (gradient w.r.t. ph, the fc_phase output) time-major [T*B][2F]
+__global__ void l2norm_pairs_bwd_kernel(const float* __restrict__ d_y, const float* __restrict__ ph,
+                                        const float* __restrict__ xp, int B, int T, int F, float* __restrict__ dz,
+                                        unsigned int* __restrict__ amax_bits) {
+  const long long total = (long long)B * T * F;
+  float am = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long bt = i / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float2 a = reinterpret_cast<const float2*>(ph)[i], r = reinterpret_cast<const float2*>(xp)[i];
+    const float2 dy = reinterpret_cast<const float2*>(d_y)[i];
+    const float re = a.x + r.x, im = a.y + r.y;
+    const float nrm = sqrtf(re * re + im * im);
+    const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+    float2 d = make_float2(dy.x * inv, dy.y * inv);
+    if (nrm > 1e-12f) {
+      const float yx = re * inv, yy = im * inv;
+      const float dot = (yx * dy.x + yy * dy.y) * inv;
+      d.x -= yx * dot;
+      d.y -= yy * dot;
+    }
+    reinterpret_cast<float2*>(dz)[((long long)t * B + b) * F + f] = d;
+    am = fmaxf(am, fmaxf(fabsf(d.x), fabsf(d.y)));
+  }
+  am = warp_max(am);
+  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_uint(am));
+}
+
+// second-BLSTM input = cat(x_mag * mask_s, x_phase): d_masks[b][t][f][s] += d_xin[t*B+b][f] * x_mag[b][t][f]
+__global__ void phase_input_bwd_kernel(const float* __restrict__ d_xin, long long ld, const float* __restrict__ x_mag,
+                                       int B, int T, int F, int S, int s_idx, float* __restrict__ d_masks) {
+  const long long total = (long long)B * T * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long bt = i / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    d_masks[i * S + s_idx] += d_xin[((long long)t * B + b) * ld + f] * x_mag[i];
+  }
+}
+
+// loss_mask_psa backward (loss_mask.py:25-40): d/dmask of sum_n |mask*noisy - min(noisy, relu(clean*cos))| per utterance
+__global__ void l1_psa_bwd_kernel(const float* __restrict__ mask, const float* __restrict__ noisy,
+                                  const float* __restrict__ clean, const float* __restrict__ cosd,
+                                  const float* __restrict__ g, int B, int N, float* __restrict__ d_mask) {
+  const long long total = (long long)B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = noisy[i];
+    const float d = mask[i] * m - fminf(m, fmaxf(clean[i] * cosd[i], 0.f));
+    d_mask[i] = (d > 0.f ? m : (d < 0.f ? -m : 0.f)) * g[i / N];
+  }
+}
+
 // middle of the enhancement model (enhancement.py:49-50), time-major [M][F]:  est = pre * mask, pre = relu(.),
 // mask = sigmoid(.):  dz_pre = d_est * mask * (pre > 0),  dz_mi = d_est * pre * mask * (1 - mask)
 __global__ void enhance_mid_bwd_kernel(const float* __restrict__ d_est, long long ld, const float* __restrict__ pre,
@@ -378,6 +469,46 @@ extern "C" int onssen_loss_mse_bwd(const float* a, const float* b, long long n, 
                                    void* stream) {
   if (!a || !b || !g || !d_a || n <= 0) return ONSSEN_ERR_ARG;
   mse_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, g, d_a);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_loss_phase_cos_bwd(const float* phase_a, const float* phase_b, const float* phase_s1,
+                                         const float* phase_s2, const float* mag_mix, const int32_t* perm,
+                                         const float* g, int B, int N, float* d_phase_a, float* d_phase_b,
+                                         void* stream) {
+  if (!phase_a || !phase_b || !phase_s1 || !phase_s2 || !mag_mix || !perm || !g || !d_phase_a || !d_phase_b ||
+      B <= 0 || N <= 0)
+    return ONSSEN_ERR_ARG;
+  phase_cos_bwd_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(
+      phase_a, phase_b, phase_s1, phase_s2, mag_mix, perm, g, B, N, d_phase_a, d_phase_b);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_l2norm_pairs_bwd(const float* d_y, const float* x, const float* residual, int B, int T, int F,
+                                       float* dz, void* amax_bits_u32, void* stream) {
+  if (!d_y || !x || !residual || !dz || !amax_bits_u32 || B <= 0 || T <= 0 || F <= 0) return ONSSEN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(amax_bits_u32, 0, 4, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+  l2norm_pairs_bwd_kernel<<<grid_for((long long)B * T * F, 256), 256, 0, s>>>(d_y, x, residual, B, T, F, dz,
+                                                                             (unsigned int*)amax_bits_u32);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_phase_input_bwd(const float* d_xin, long long ld, const float* x_mag, int B, int T, int F,
+                                      int S, int s_idx, float* d_masks, void* stream) {
+  if (!d_xin || !x_mag || !d_masks || B <= 0 || T <= 0 || F <= 0 || S <= 0 || s_idx < 0 || s_idx >= S || ld < F)
+    return ONSSEN_ERR_ARG;
+  phase_input_bwd_kernel<<<grid_for((long long)B * T * F, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_xin, ld, x_mag, B, T, F, S, s_idx, d_masks);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_loss_l1_psa_bwd(const float* mask, const float* mag_noisy, const float* mag_clean,
+                                      const float* cos_diff, const float* g, int B, int N, float* d_mask,
+                                      void* stream) {
+  if (!mask || !mag_noisy || !mag_clean || !cos_diff || !g || !d_mask || B <= 0 || N <= 0) return ONSSEN_ERR_ARG;
+  l1_psa_bwd_kernel<<<grid_for((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(mask, mag_noisy, mag_clean,
+                                                                                       cos_diff, g, B, N, d_mask);
   return ONSSEN_CHECK_LAUNCH();
 }
 

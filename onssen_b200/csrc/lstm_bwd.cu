@@ -24,7 +24,17 @@ struct BwdParams {
   int B, T, H, Hp, s;
   float dropout_p;
   unsigned int seed_lo, seed_hi;
+  long long* trace;     // debug: clock64 stamps of CTA (0,0,0), steps [BWD_TRACE_S0, +8): [step][slot 0..7][warp 0..7]
 };
+
+long long* g_bwd_trace = nullptr;
+#define BWD_TRACE_S0 100
+#define BWD_TRACE(slot)                                                                                          \
+  do {                                                                                                           \
+    if (p.trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0 &&          \
+        s >= BWD_TRACE_S0 && s < BWD_TRACE_S0 + 8)                                                               \
+      p.trace[(s - BWD_TRACE_S0) * 64 + (slot) * 8 + (threadIdx.x >> 5)] = clock64();                            \
+  } while (0)
 
 __device__ __forceinline__ float hash_uniform32(unsigned int seed_lo, unsigned int seed_hi, unsigned int idx) {
   unsigned int x = idx ^ seed_lo;
@@ -184,16 +194,35 @@ __device__ __forceinline__ __half to_half_flag_range(float x) {   // clamp to th
   return __float2half_rn(x);
 }
 
+// NT = 8-column n-tiles per batch block (2 -> 16 utterances per CTA, 4 -> 32): the launcher takes the smallest NT whose
+// grid still fits one CTA per SM, so that at B=32, H=600 76 CTAs share the work instead of 38.
+//
+// Step anatomy (measured, scripts/bwd_trace.py, profiles/r01_bwd_step_trace.txt): the exchange wait dominates --
+// every CTA pulls the whole dG of its (direction, batch block), 4Hp x NB fp16 = 78 KB at NT=2, through its own
+// L2->SM port each step.  So (1) a burst that comes back stale wastes a full transfer: one fragment per producer
+// CTA is probed first and the burst (KPW k-steps x NT fragments per lane, ONE L2 round trip) is only issued
+// when the probes carry the step's flag bits; (2) everything of the gate math that does not depend on dh_rec
+// (tanh, dropout, the products of saved activations) is computed while the burst is in flight, which leaves
+// ~10 dependent instructions between the partial-sum barrier and the publish stores; (3) the publish stores go
+// before the dG stores that only the later GEMMs read.
+template <int NT>
 __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdParams p) {
+  constexpr int KPW = NT == 2 ? 19 : 8;      // fragment k-steps held in registers at once (NT*KPW uint2 per lane)
+  constexpr int NB = 8 * NT;                  // batch columns per CTA
+  constexpr int ITEMS = NT;                   // (unit, batch) pairs per thread: 32 * NB / 256
   extern __shared__ __align__(16) uint8_t bsm[];
   const int Hp = p.Hp, B = p.B, T = p.T;
   const int G4 = 4 * Hp;
   const int ksteps = G4 / 16;
   uint4* a_s = reinterpret_cast<uint4*>(bsm);                                   // [ksteps][2][32] uint4
-  float (*red)[32][33] = reinterpret_cast<float (*)[32][33]>(bsm + (size_t)ksteps * 2 * 32 * 16);
+  // partial sums of the 8 K-split warps in accumulator-fragment order, double-buffered over steps:
+  // red[step parity][source warp][tile = mt*NT + nt][lane] = that lane's 4 accumulators (one STS.128 per tile;
+  // a __syncthreads drains pending shared stores at ~36 cycles each with 8 warps, so their COUNT is what matters)
+  float4* red = reinterpret_cast<float4*>(bsm + (size_t)ksteps * 2 * 32 * 16);
+  constexpr int RED_STEP = 8 * 2 * NT * 32;   // float4 per parity
   const int ub = blockIdx.x, dir = blockIdx.y, bb = blockIdx.z;
   const int nub = Hp / 32, nbb = gridDim.z;
-  const int b0 = bb * 32;
+  const int b0 = bb * NB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
   const float inv_scale = p.scale2[1], scale = p.scale2[0];
@@ -207,140 +236,220 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
   const int per_warp = (ksteps + 7) / 8;
   const int ks_begin = warp * per_warp;
   const int ks_end = min(ksteps, ks_begin + per_warp);
-  const size_t frag_group = (size_t)ksteps * 4 * 32;   // uint2 per (parity, dir, bb)
+  const size_t frag_group = (size_t)ksteps * NT * 32;   // uint2 per (parity, dir, bb)
+  float dc_carry[ITEMS];                                 // cell-gradient carry of this thread's (unit, batch) pairs
+  // this thread's publish slots (word offsets inside one (parity, dir, bb) fragment group) and output offsets
+  unsigned int pub_off[ITEMS];
+  long long row_off[ITEMS];
+  // phase-B ownership follows the accumulator fragments: warp -> tile (mt, nt) and which of the lane's 4 values
+  // (NT=2: two warps share a tile, rows g / g+8; NT=4: one warp per tile, all 4 values)
+  const int my_tile = warp / (4 / NT), my_v0 = (warp % (4 / NT)) * NT;
+  int item_ul[ITEMS], item_bl[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    dc_carry[i] = 0.f;
+    const int v = my_v0 + i;                      // value index inside the m16n8 accumulator fragment
+    const int ul = (my_tile / NT) * 16 + g + 8 * (v >> 1), bl = (my_tile % NT) * 8 + 2 * tq + (v & 1);
+    item_ul[i] = ul;
+    item_bl[i] = bl;
+    const int ks = ub * 8 + (ul >> 2);
+    const int j = ul & 3;
+    // row r = ub*128 + 4*ul + gate is k-index 4*j + gate of k-step ks; word pair (2 gates) -> register j>>1
+    pub_off[i] = (unsigned int)((((size_t)ks * NT + (bl >> 3)) * 32 + (bl & 7) * 4 + (j & 1) * 2) * 2 + (j >> 1));
+    row_off[i] = (long long)min(b0 + bl, B - 1) * (2 * G4) + dir * G4 + ub * 128 + 4 * ul;
+  }
 
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? T - 1 - s : s;
     const int t_fp = dir == 0 ? t - 1 : t + 1;
+    BWD_TRACE(0);
     // ---- per-step inputs that do not depend on the recurrence: issue their loads before the exchange wait
-    float4 a4[4];
-    float ct[4], cprev[4], dyv[4];
-    long long oyv[4];
+    float4 a4[ITEMS];
+    float ct[ITEMS], cprev[ITEMS], dyv[ITEMS];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + 256 * i;
-      const int ul = idx & 31, bl = idx >> 5;
+    for (int i = 0; i < ITEMS; ++i) {
+      const int ul = item_ul[i], bl = item_bl[i];
       const int b = min(b0 + bl, B - 1);               // clamped: results of pad columns are replaced by zeros
       const int u = ub * 32 + ul;
-      const long long m = (long long)t * B + b;
-      oyv[i] = m * (2 * Hp) + dir * Hp + u;
-      a4[i] = *reinterpret_cast<const float4*>(p.actg + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul);
-      ct[i] = p.c[oyv[i]];
+      const long long oy = ((long long)t * B + b) * (2 * Hp) + dir * Hp + u;
+      a4[i] = *reinterpret_cast<const float4*>(p.actg + (long long)t * B * (2 * G4) + row_off[i]);
+      ct[i] = p.c[oy];
       cprev[i] = (t_fp >= 0 && t_fp < T) ? p.c[((long long)t_fp * B + b) * (2 * Hp) + dir * Hp + u] : 0.f;
-      dyv[i] = p.dy[oyv[i]];
+      dyv[i] = p.dy[oy];
+      if (p.dropout_p > 0.f) {   // the dropout decision only needs the index: fold it into a multiplier now
+        const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)oy);
+        dyv[i] *= rnd < p.dropout_p ? 0.f : keep_scale;
+      }
     }
+    // factors of the gate derivatives that do not depend on dh_rec:
+    //   dh = dy + dh_rec;  dct = dh*k_c + carry;  (di, df, dg) = dct*(k_i, k_f, k_g);  do = dh*k_o;  carry' = dct*f
+    float k_c[ITEMS], k_i[ITEMS], k_f[ITEMS], k_g[ITEMS], k_o[ITEMS], f_g[ITEMS];
+    auto gate_factors = [&]() {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const float tc = tanhf(ct[i]);
+        k_c[i] = a4[i].w * (1.0f - tc * tc);
+        k_i[i] = a4[i].z * a4[i].x * (1.0f - a4[i].x) * scale;
+        k_f[i] = cprev[i] * a4[i].y * (1.0f - a4[i].y) * scale;
+        k_g[i] = a4[i].x * (1.0f - a4[i].z * a4[i].z) * scale;
+        k_o[i] = tc * a4[i].w * (1.0f - a4[i].w) * scale;
+        f_g[i] = a4[i].y;
+      }
+    };
     // ---- phase A: dh_rec = W_hh^T slice x dG_{previous step} (all gate rows of this direction)
     if (s > 0) {
-      float acc[2][4][4];
+      float acc[2][NT][4];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NT; ++j)
 #pragma unroll
           for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
       const unsigned int fbit = ((((unsigned int)(s - 1)) >> 1) & 1u) ^ 1u;
       const unsigned int fw = fbit ? 0x40004000u : 0u;
       const uint2* bfr = reinterpret_cast<const uint2*>(p.frag) +
                          (((size_t)((s - 1) & 1) * 2 + dir) * nbb + bb) * frag_group + lane;
-      constexpr int U = 4;
-      for (int ksb = ks_begin; ksb < ks_end; ksb += U) {
-        uint2 bf[U][4];
-        unsigned int pending = 0;
+      for (int ksb = ks_begin; ksb < ks_end; ksb += KPW) {
+        const int kse = min(ksb + KPW, ks_end);
+        {
+          // probe: the last-written n-tile of one fragment per producer CTA (8 k-steps each) of this k-range
+          unsigned int probe = 0;
 #pragma unroll
-        for (int uu = 0; uu < U; ++uu)
-          if (ksb + uu < ks_end) pending |= 0xFu << (4 * uu);
-        while (pending) {
+          for (int q = 0; q < 4; ++q)
+            if (max(ksb, ((ksb >> 3) + q) * 8) < kse) probe |= 1u << q;
+          while (probe) {
+            uint2 pv[4];
 #pragma unroll
-          for (int uu = 0; uu < U; ++uu)
+            for (int q = 0; q < 4; ++q)
+              if (probe & (1u << q))
+                pv[q] = ld_relaxed_v2(bfr + ((size_t)max(ksb, ((ksb >> 3) + q) * 8) * NT + (NT - 1)) * 32);
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-              if (pending & (1u << (4 * uu + nt))) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * 4 + nt) * 32);
+            for (int q = 0; q < 4; ++q)
+              if ((probe & (1u << q)) && (pv[q].x & 0x40004000u) == fw && (pv[q].y & 0x40004000u) == fw)
+                probe &= ~(1u << q);
+          }
+        }
+        uint2 bf[KPW][NT];
+        unsigned long long pending = 0;
 #pragma unroll
-          for (int uu = 0; uu < U; ++uu)
+        for (int uu = 0; uu < KPW; ++uu)
+          if (ksb + uu < kse) pending |= (unsigned long long)((1u << NT) - 1u) << (NT * uu);
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-              if ((pending & (1u << (4 * uu + nt))) && (bf[uu][nt].x & 0x40004000u) == fw &&
+        for (int uu = 0; uu < KPW; ++uu)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+            if (pending & (1ull << (NT * uu + nt))) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * NT + nt) * 32);
+        if (ksb == ks_begin) gate_factors();   // overlaps the burst's round trip
+        while (true) {
+#pragma unroll
+          for (int uu = 0; uu < KPW; ++uu)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+              if ((pending & (1ull << (NT * uu + nt))) && (bf[uu][nt].x & 0x40004000u) == fw &&
                   (bf[uu][nt].y & 0x40004000u) == fw) {
                 bf[uu][nt].x &= ~0x40004000u;
                 bf[uu][nt].y &= ~0x40004000u;
-                pending &= ~(1u << (4 * uu + nt));
+                pending &= ~(1ull << (NT * uu + nt));
               }
+          if (!pending) break;
+#pragma unroll
+          for (int uu = 0; uu < KPW; ++uu)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+              if (pending & (1ull << (NT * uu + nt))) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * NT + nt) * 32);
         }
+        BWD_TRACE(1);
+        // A fragments double-buffered in registers: the shared-memory load of k-step uu+1 is in flight during the
+        // MMAs of k-step uu
+        uint4 an0 = a_s[((size_t)ksb * 2 + 0) * 32 + lane];
+        uint4 an1 = a_s[((size_t)ksb * 2 + 1) * 32 + lane];
 #pragma unroll
-        for (int uu = 0; uu < U; ++uu) {
-          if (ksb + uu < ks_end) {
-            const uint4 a0 = a_s[((size_t)(ksb + uu) * 2 + 0) * 32 + lane];
-            const uint4 a1 = a_s[((size_t)(ksb + uu) * 2 + 1) * 32 + lane];
+        for (int uu = 0; uu < KPW; ++uu) {
+          if (ksb + uu < kse) {
+            const uint4 a0 = an0, a1 = an1;
+            const int kn = min(ksb + uu + 1, ks_end - 1);
+            an0 = a_s[((size_t)kn * 2 + 0) * 32 + lane];
+            an1 = a_s[((size_t)kn * 2 + 1) * 32 + lane];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int nt = 0; nt < NT; ++nt) {
               mma_16816(acc[0][nt], reinterpret_cast<const uint32_t*>(&a0), reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
               mma_16816(acc[1][nt], reinterpret_cast<const uint32_t*>(&a1), reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
             }
           }
         }
       }
+      BWD_TRACE(5);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          red[warp][mt * 16 + g][nt * 8 + 2 * tq] = acc[mt][nt][0];
-          red[warp][mt * 16 + g][nt * 8 + 2 * tq + 1] = acc[mt][nt][1];
-          red[warp][mt * 16 + g + 8][nt * 8 + 2 * tq] = acc[mt][nt][2];
-          red[warp][mt * 16 + g + 8][nt * 8 + 2 * tq + 1] = acc[mt][nt][3];
-        }
+        for (int nt = 0; nt < NT; ++nt)
+          red[(s & 1) * RED_STEP + (warp * 2 * NT + mt * NT + nt) * 32 + lane] =
+              make_float4(acc[mt][nt][0], acc[mt][nt][1], acc[mt][nt][2], acc[mt][nt][3]);
+    } else {
+      gate_factors();
     }
+    BWD_TRACE(2);
     __syncthreads();
+    BWD_TRACE(3);
     // ---- phase B: gate derivatives of this CTA's units at step t; publish dG in B-fragment order
     const unsigned int fbit_w = ((((unsigned int)s) >> 1) & 1u) ^ 1u;
     const unsigned int fww = fbit_w ? 0x40004000u : 0u;
+    uint32_t* fb = p.frag + (((size_t)(s & 1) * 2 + dir) * nbb + bb) * frag_group * 2;
+    float4 d4v[ITEMS];
+    uint2 ov[ITEMS];
+    float rsum[ITEMS];
+    if (s > 0) {
+      const float* rp = reinterpret_cast<const float*>(red + (s & 1) * RED_STEP + my_tile * 32 + lane) + my_v0;
+      float r[8][ITEMS];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + 256 * i;
-      const int ul = idx & 31, bl = idx >> 5;
-      const bool valid = (b0 + bl) < B;
-      const int u = ub * 32 + ul;
-      float dh_rec = 0.f;
-      if (s > 0) {
+      for (int w = 0; w < 8; ++w) {
+        if (NT == 2) {
+          const float2 v = *reinterpret_cast<const float2*>(rp + (size_t)w * 2 * NT * 32 * 4);
+          r[w][0] = v.x; r[w][1] = v.y;
+        } else {
+          const float4 v = *reinterpret_cast<const float4*>(rp + (size_t)w * 2 * NT * 32 * 4);
+          r[w][0] = v.x; r[w][1] = v.y; r[w][ITEMS - 2] = v.z; r[w][ITEMS - 1] = v.w;
+        }
+      }
 #pragma unroll
-        for (int w = 0; w < 8; ++w) dh_rec += red[w][ul][bl];
-        dh_rec *= inv_scale;
-      }
-      float dy = dyv[i];
-      if (p.dropout_p > 0.f) {
-        const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)oyv[i]);
-        dy = rnd < p.dropout_p ? 0.f : dy * keep_scale;
-      }
-      const float dh = dy + dh_rec;
-      const float tc = tanhf(ct[i]);
-      float* dcp = p.dc + ((size_t)dir * B + min(b0 + bl, B - 1)) * Hp + u;
-      const float dct = dh * a4[i].w * (1.0f - tc * tc) + ((s > 0 && valid) ? *dcp : 0.f);
-      float4 d4;
-      d4.x = dct * a4[i].z * a4[i].x * (1.0f - a4[i].x);
-      d4.y = dct * cprev[i] * a4[i].y * (1.0f - a4[i].y);
-      d4.z = dct * a4[i].x * (1.0f - a4[i].z * a4[i].z);
-      d4.w = dh * tc * a4[i].w * (1.0f - a4[i].w);
+      for (int i = 0; i < ITEMS; ++i)
+        rsum[i] = (((r[0][i] + r[1][i]) + (r[2][i] + r[3][i])) + ((r[4][i] + r[5][i]) + (r[6][i] + r[7][i]))) * inv_scale;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int bl = item_bl[i];
+      float dh = dyv[i];
+      if (s > 0) dh += rsum[i];
+      const float dct = dh * k_c[i] + dc_carry[i];
+      dc_carry[i] = dct * f_g[i];
+      // scaled values (the k_* carry the loss scale); the fp32 copy is unscaled again below
+      const float s_i = dct * k_i[i], s_f = dct * k_f[i], s_g = dct * k_g[i], s_o = dh * k_o[i];
       uint2 o = make_uint2(0u, 0u);
-      if (valid) {
-        *dcp = dct * a4[i].y;
-        const long long m = (long long)t * B + b0 + bl;
-        *reinterpret_cast<float4*>(p.actg + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul) = d4;
-        __half2 lo = __halves2half2(to_half_flag_range(d4.x * scale), to_half_flag_range(d4.y * scale));
-        __half2 hi = __halves2half2(to_half_flag_range(d4.z * scale), to_half_flag_range(d4.w * scale));
+      if ((b0 + bl) < B) {   // pad batch columns publish zeros so that every fragment entry turns fresh
+        __half2 lo = __halves2half2(to_half_flag_range(s_i), to_half_flag_range(s_f));
+        __half2 hi = __halves2half2(to_half_flag_range(s_g), to_half_flag_range(s_o));
         o.x = *reinterpret_cast<uint32_t*>(&lo);
         o.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(p.dg16 + m * (2 * G4) + dir * G4 + ub * 128 + 4 * ul) = o;
       }
-      if (s + 1 < T) {   // pad batch columns publish zeros so that every fragment entry becomes fresh
-        const int ks = ub * 8 + (ul >> 2);
-        const int j = ul & 3;
-        const int reg = j >> 1;
-        const int tq0 = (j & 1) * 2;
-        uint32_t* fb = p.frag + ((((size_t)(s & 1) * 2 + dir) * nbb + bb) * frag_group + ((size_t)ks * 4 + (bl >> 3)) * 32) * 2;
-        st_relaxed_u32(fb + ((bl & 7) * 4 + tq0) * 2 + reg, o.x | fww);
-        st_relaxed_u32(fb + ((bl & 7) * 4 + tq0 + 1) * 2 + reg, o.y | fww);
+      if (s + 1 < T) {       // the exchange first: it is on the critical path of every CTA of this direction
+        st_relaxed_u32(fb + pub_off[i], o.x | fww);
+        st_relaxed_u32(fb + pub_off[i] + 2, o.y | fww);
+      }
+      d4v[i] = make_float4(s_i * inv_scale, s_f * inv_scale, s_g * inv_scale, s_o * inv_scale);
+      ov[i] = o;
+    }
+    BWD_TRACE(6);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      if ((b0 + item_bl[i]) < B) {
+        const long long off = (long long)t * B * (2 * G4) + row_off[i];
+        *reinterpret_cast<float4*>(p.actg + off) = d4v[i];
+        *reinterpret_cast<uint2*>(p.dg16 + off) = ov[i];
       }
     }
-    __syncthreads();   // red[] is rewritten by the next step's phase A
+    BWD_TRACE(4);
+    // no second barrier: red[] is double-buffered, and a warp can only reach its write of step s+2 after the
+    // barrier of step s+1, which every warp passes after its reads of step s
   }
 }
 
@@ -386,6 +495,7 @@ extern "C" int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, 
 }
 
 extern "C" void onssen_blstm_rec_bwd_set_persistent(int on) { g_bwd_persistent = on ? 1 : 0; }
+extern "C" void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64) { g_bwd_trace = (long long*)device_buf_512_int64; }
 
 extern "C" size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H) {
   const int Hp = hp_of(H);
@@ -409,26 +519,28 @@ extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c
   p.seed_hi = (unsigned int)(mix >> 32);
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch, 0, onssen_blstm_rec_bwd_scratch_bytes(B, H), s) != cudaSuccess) return ONSSEN_ERR_CUDA;
-  dim3 grid(p.Hp / 32, 2, (B + 31) / 32);
+  p.trace = g_bwd_trace;
   // persistent path: W_hh^T fragments resident in smem, one cooperative launch for all T steps
-  {
-    const size_t smem = (size_t)(4 * p.Hp / 16) * 2 * 32 * 16 + (size_t)8 * 32 * 33 * sizeof(float);
-    const int nblocks = (int)(grid.x * grid.y * grid.z);
-    if (g_bwd_persistent && smem <= 225 * 1024 && nblocks <= num_sms()) {
-      if (cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-          cudaSuccess)
+  if (g_bwd_persistent) {
+    for (int nt = 2; nt <= 4; nt += 2) {
+      const int nb = 8 * nt;
+      dim3 pgrid(p.Hp / 32, 2, (B + nb - 1) / nb);
+      const size_t smem = (size_t)(4 * p.Hp / 16) * 2 * 32 * 16 + (size_t)2 * 8 * 2 * nt * 32 * 16;
+      const int nblocks = (int)(pgrid.x * pgrid.y * pgrid.z);
+      if (smem > 225 * 1024 || nblocks > num_sms()) continue;
+      const void* fn = nt == 2 ? (const void*)lstm_bwd_persistent_kernel<2> : (const void*)lstm_bwd_persistent_kernel<4>;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return ONSSEN_ERR_CUDA;
       int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persistent_kernel, 256, smem) == cudaSuccess &&
-          per_sm * num_sms() >= nblocks) {
-        void* args[] = {(void*)&p};
-        if (cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_kernel, grid, dim3(256), args, smem, s) !=
-            cudaSuccess)
-          return ONSSEN_ERR_CUDA;
-        return ONSSEN_OK;
-      }
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem) != cudaSuccess ||
+          per_sm * num_sms() < nblocks)
+        continue;
+      void* args[] = {(void*)&p};
+      if (cudaLaunchCooperativeKernel(fn, pgrid, dim3(256), args, smem, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+      return ONSSEN_OK;
     }
   }
+  dim3 grid(p.Hp / 32, 2, (B + 31) / 32);
   for (int step = 0; step < T; ++step) {
     p.s = step;
     lstm_bwd_step_kernel<<<grid, 256, 0, s>>>(p);

@@ -26,18 +26,20 @@ class _PitL1(torch.autograd.Function):
         out, perm = _lib.loss_pit_l1_fwd(ma, mb, stride, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2)
         ctx.save_for_backward(ma, mb, mag_mix, mag_s1, mag_s2, cos_s1, cos_s2, perm)
         ctx.stride = stride
-        return out
+        ctx.mark_non_differentiable(perm)
+        return out, perm
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _g_perm):
         ma, mb, mix, s1, s2, c1, c2, perm = ctx.saved_tensors
         da, db = _lib.loss_pit_l1_bwd(ma, mb, ctx.stride, mix, s1, s2, c1, c2, perm, g)
         return da, db, None, None, None, None, None
 
 
-def _pit(mask_A, mask_B, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None):
+def _pit(mask_A, mask_B, mag_mix, mag_s1, mag_s2, cos_s1=None, cos_s2=None, want_perm=False):
     c = lambda t: None if t is None else t.detach().float().contiguous()
-    return _PitL1.apply(mask_A, mask_B, c(mag_mix), c(mag_s1), c(mag_s2), c(cos_s1), c(cos_s2))
+    out, perm = _PitL1.apply(mask_A, mask_B, c(mag_mix), c(mag_s1), c(mag_s2), c(cos_s1), c(cos_s2))
+    return (out, perm) if want_perm else out
 
 
 def loss_chimera_msa(output, label):

@@ -24,10 +24,22 @@ def loss_mask_msa(output, label):
     return _MSE.apply(clean_est.float().contiguous(), mag_clean.detach().float().contiguous())
 
 
+class _L1Psa(torch.autograd.Function):
+    """per-utterance L1 of mask*noisy - min(noisy, relu(clean*cos)) with a hand-written backward w.r.t. mask."""
+
+    @staticmethod
+    def forward(ctx, mask, noisy, clean, cosd):
+        ctx.save_for_backward(mask, noisy, clean, cosd)
+        return _lib.loss_l1_psa_fwd(mask, noisy, clean, cosd)
+
+    @staticmethod
+    def backward(ctx, g):
+        mask, noisy, clean, cosd = ctx.saved_tensors
+        return _lib.loss_l1_psa_bwd(mask, noisy, clean, cosd, g), None, None, None
+
+
 def loss_mask_psa(output, label):
     [mask] = output
     [mag_noisy, mag_clean, cos_diff] = label
     c = lambda t: t.detach().float().contiguous()
-    if torch.is_grad_enabled() and mask.requires_grad:
-        raise NotImplementedError("loss_mask_psa backward is not part of this build (use loss_mask_msa for training)")
-    return _lib.loss_l1_psa_fwd(c(mask), c(mag_noisy), c(mag_clean), c(cos_diff))
+    return _L1Psa.apply(mask.float().contiguous(), c(mag_noisy), c(mag_clean), c(cos_diff))

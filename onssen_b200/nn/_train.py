@@ -13,13 +13,18 @@ from ._blstm import _next_seed, lstm_layer_params, pack_lstm
 
 # ------------------------------------------------------------------------------------------------ shared pieces
 def blstm_forward_train(rnn, cache, x, training, last_f32):
-    """Returns (layers, y_last) where y_last is fp32 [M][2Hp] (last_f32) or fp16; layers hold the BPTT state."""
+    """Returns (layers, packed, y_last) where y_last is fp32 [M][2Hp] (last_f32) or fp16; layers hold the BPTT state."""
     B, T, _ = x.shape
+    return blstm_forward_train_packed(rnn, cache, _lib.pack_input_f16(x.contiguous()), B, T, training, last_f32)
+
+
+def blstm_forward_train_packed(rnn, cache, a, B, T, training, last_f32):
+    """Same, from an already packed time-major fp16 input a [T*B][Kp]."""
+    x = a
     H, L = rnn.hidden_size, rnn.num_layers
     Hp, M = _lib.hp_of(H), T * B
     params = [p for l in range(L) for d in lstm_layer_params(rnn, l) for p in d]
     packed = cache.get(params, lambda: pack_lstm(rnn))
-    a = _lib.pack_input_f16(x.contiguous())
     ws = _lib.blstm_rec_workspace(B, H, x.device)
     layers, y_h, y_f = [], None, None
     for l in range(L):
@@ -61,7 +66,8 @@ def linear_backward(dz32, sc, a_in_h, w_p, N, H, grads, name, K=None, want_dA=Tr
     return dA
 
 
-def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None):
+def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None, want_dx0=False):
+    """BPTT through the stack.  Returns grads, or (grads, dX0 fp32 [M][Kp of layer 0]) with want_dx0."""
     H, L = rnn.hidden_size, rnn.num_layers
     Hp, M = _lib.hp_of(H), T * B
     Mp = _lib.pad64(M)
@@ -95,7 +101,7 @@ def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None):
             dWhh_p = torch.empty(4 * Hp, Hp, device=dev, dtype=torch.float32)
             _lib.gemm_f16_ex(dgT[d * 4 * Hp:(d + 1) * 4 * Hp], hT, None, dWhh_p, 4 * Hp, Hp, Mp, Hp, out_scale=inv)
             grads[f"{prefix}weight_hh_l{l}{suf}"] = _lib.unpack_lstm_grad(dWhh_p, H, H, False, 0, 0)
-        if l > 0:
+        if l > 0 or want_dx0:
             wihT = _lib.transpose_shift_f16(wih_p, 0, kp_in)
             dX = torch.empty(M, kp_in, device=dev, dtype=torch.float32)
             _lib.gemm_f16_ex(dg16, wihT, None, dX, M, kp_in, 8 * Hp, kp_in, out_scale=inv)
@@ -104,7 +110,7 @@ def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None):
         if on_grads is not None:
             # bias_ih / bias_hh share one tensor: reduce it once
             on_grads({k: v for k, v in grads.items() if k not in done_before and "bias_hh" not in k})
-    return grads
+    return (grads, dY) if want_dx0 else grads
 
 
 class _ModelFunction(torch.autograd.Function):
@@ -269,3 +275,74 @@ def enhance_backward(model, saved, d_outs, on_grads=None):
     if on_grads is not None:
         on_grads(dict(grads))
     return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)
+
+
+# ------------------------------------------------------------------------------------------------ phase_net (repaired)
+def phase_forward_train(model, inp):
+    x_mag, x_phase = inp
+    ch = model.chimera
+    (emb, masks), saved_ch = chimera_forward_train(ch, x_mag)
+    B, T, F = x_mag.shape
+    H = model.hidden_dim
+    M = T * B
+    bn = model.bn
+    w_ph = model._ph.get([model.fc_phase.weight], lambda: _lib.pack_linear_f16(model.fc_phase.weight, True, H))
+    branches, outs = [], []
+    for s_idx in range(2):
+        mk = masks[:, :, :, s_idx]
+        xin = _lib.pack_phase_input_f16(x_mag, mk, mk.stride(-1), x_phase)
+        layers, packed, y_f = blstm_forward_train_packed(model.rnn, model._rnn_cache, xin, B, T, model.training, True)
+        a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                                                bn.running_var, bn.eps, bn.momentum, True, save_stats=True)
+        bn.num_batches_tracked += 1
+        ph = torch.empty(B, T, F, 2, device=x_mag.device, dtype=torch.float32)
+        _lib.gemm_f16(a_h, w_ph, model.fc_phase.bias.detach(), ph, M, 2 * F, a_h.shape[1], 2 * F, remap_inner=B,
+                      remap_outer=T)
+        outs.append(_lib.add_l2norm_pairs(ph, x_phase))
+        branches.append(dict(layers=layers, packed=packed, y_f=y_f, a_h=a_h, mean=mean, invstd=invstd, ph=ph))
+    saved = dict(ch=saved_ch, branches=branches, x_mag=x_mag, x_phase=x_phase, w_ph=w_ph, shape=(B, T, F))
+    return (emb, masks, outs[0], outs[1]), saved
+
+
+def phase_backward(model, saved, d_outs, on_grads=None):
+    d_emb, d_masks, d_pa, d_pb = d_outs
+    B, T, F = saved["shape"]
+    H = model.hidden_dim
+    M = T * B
+    bn = model.bn
+    dev = saved["x_mag"].device
+    S = 2
+    d_masks = torch.zeros(B, T, F, S, device=dev, dtype=torch.float32) if d_masks is None else d_masks.clone()
+    total = None
+    for s_idx, d_p in enumerate((d_pa, d_pb)):
+        if d_p is None:
+            continue
+        br = saved["branches"][s_idx]
+        g = {}
+        dz, sc = _lib.l2norm_pairs_bwd(d_p, br["ph"], saved["x_phase"])
+        dA = linear_backward(dz, sc, br["a_h"], saved["w_ph"], 2 * F, H, g, "fc_phase")
+        dY, g["bn.weight"], g["bn.bias"] = _lib.bn_backward(dA, br["y_f"], M, H, bn.weight.detach(), br["mean"],
+                                                            br["invstd"])
+        g, d_xin = blstm_backward(model.rnn, br["layers"], br["packed"], dY, B, T, g, "rnn.", None, want_dx0=True)
+        _lib.phase_input_bwd(d_xin, saved["x_mag"], d_masks, s_idx)
+        if total is None:
+            total = g
+        else:                                  # shared weights: the two passes add up
+            done = set()
+            for k, v in g.items():
+                if v.data_ptr() not in done:    # bias_ih / bias_hh share one tensor
+                    _lib.add_inplace(total[k], v)
+                    done.add(v.data_ptr())
+    if total is None:
+        total = {n: torch.zeros_like(p) for n, p in model.named_parameters() if not n.startswith("chimera.")}
+    g_ch = chimera_backward(model.chimera, saved["ch"], [d_emb, d_masks], None)
+    grads = dict(total)
+    grads.update({"chimera." + k: v for k, v in g_ch.items()})
+    if on_grads is not None:
+        seen, uniq = set(), {}
+        for k, v in grads.items():
+            if v.data_ptr() not in seen:
+                uniq[k] = v
+                seen.add(v.data_ptr())
+        on_grads(uniq)
+    return grads

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward, require_no_grad
+from ._blstm import PackCache
 from .chimera import chimera
 
 
@@ -47,7 +47,13 @@ class phase_net(nn.Module):
         x_mag, x_phase = input
         x_mag = x_mag.float().contiguous()
         x_phase = x_phase.float().contiguous()
-        require_no_grad("phase_net", x_mag, self.fc_phase.weight)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if not self.training:
+                raise NotImplementedError("phase_net: gradients are implemented for train() mode (batch-statistics "
+                                          "BatchNorm), call model.train()")
+            from ._train import phase_backward, phase_forward_train, run_model
+            emb, masks, p_a, p_b = run_model(self, phase_forward_train, phase_backward, (x_mag, x_phase))
+            return [emb, masks[:, :, :, 0], masks[:, :, :, 1], p_a, p_b]
         embedding, mask_A, mask_B = self.chimera([x_mag])
         B, T, F = mask_A.shape
         outs = []

@@ -138,5 +138,79 @@ def main():
         print("wrote", name)
 
 
+def main_phase():
+    """phase_net / loss_phase fixtures.  The reference classes raise as written (phase_network.py:28,
+    loss_phase.py:7-13), so these come from a torch RESTATEMENT WITH THE REPAIRS of SURVEY.md 8a-14/a18 built on the
+    live reference chimera + loss_dc: they pin our CUDA path and the numpy oracle to each other and to torch autograd,
+    not to the (non-running) reference -> "parity unpinned" for these two rows."""
+    import torch
+    import torch.nn.functional as Fn
+    onssen = import_reference()
+    out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+    torch.manual_seed(20260925)
+    rng = np.random.RandomState(11)
+
+    class PhaseNetRepaired(torch.nn.Module):
+        def __init__(self, F, H, L, D):
+            super().__init__()
+            self.rnn = torch.nn.LSTM(3 * F, H, L, dropout=0.0, bidirectional=True, batch_first=True)
+            self.bn = torch.nn.BatchNorm1d(2 * H)
+            self.fc_phase = torch.nn.Linear(2 * H, 2 * F)         # repair: output_dim := num_speaker * input_dim
+            self.chimera = onssen.nn.chimera(F, H, L, D, dropout=0.0)
+
+        def forward(self, inp):
+            x_mag, x_phase = inp
+            emb, m_a, m_b = self.chimera([x_mag])
+            B, T, F = m_a.shape
+            outs = []
+            for m in (m_a, m_b):
+                y, _ = self.rnn(torch.cat((x_mag * m, x_phase.reshape(B, T, -1)), 2))
+                y = self.bn(y.permute(0, 2, 1)).permute(0, 2, 1)
+                outs.append(Fn.normalize(self.fc_phase(y).reshape(B, T, F, -1) + x_phase, p=2, dim=-1))
+            return [emb, m_a, m_b] + outs
+
+    def loss_phase_repaired(output, label):
+        emb, m_a, m_b, p_a, p_b = output                           # repair: 5 outputs
+        oh, mix, s1, s2, ph1, ph2 = label
+        B = mix.shape[0]
+        l_emb = onssen.loss.loss_dc([emb], [oh, mix])              # repair: mag_mix belongs to the label list
+        l1n = lambda x: x.abs().reshape(B, -1).sum(1)
+        lm1 = l1n(m_a * mix - s1) + l1n(m_b * mix - s2)
+        lm2 = l1n(m_b * mix - s1) + l1n(m_a * mix - s2)
+        cs = lambda a, b: Fn.cosine_similarity(a, b, dim=3)
+        lp1 = (-mix * cs(p_a, ph1) - mix * cs(p_b, ph2)).reshape(B, -1).sum(1)
+        lp2 = (-mix * cs(p_b, ph1) - mix * cs(p_a, ph2)).reshape(B, -1).sum(1)
+        first = lm1 < lm2
+        return l_emb * 0.975 + torch.where(first, lm1, lm2) * 0.025 + torch.where(first, lp1, lp2) * 0.025
+
+    cases = {"small": dict(B=3, T=16, F=9, H=8, L=2, D=4), "mid": dict(B=2, T=24, F=33, H=40, L=2, D=20)}
+    for name, c in cases.items():
+        B, T, F, H, L, D = (c[k] for k in "BTFHLD")
+        feat, oh, mix, mag1, mag2, _, _ = make_labels(rng, B, T, F)
+        x_phase = (rng.standard_normal((B, T, F, 2)) * mix[..., None]).astype(np.float32)
+        ph1 = (rng.standard_normal((B, T, F, 2)) * mag1[..., None]).astype(np.float32)
+        ph2 = (rng.standard_normal((B, T, F, 2)) * mag2[..., None]).astype(np.float32)
+        tt = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        net = PhaseNetRepaired(F, H, L, D)
+        rand_bn(net, torch)
+        sd = sd_to_np(net.state_dict())
+        net.train()
+        out = net([tt(feat), tt(x_phase)])
+        loss = loss_phase_repaired(out, [tt(oh), tt(mix), tt(mag1), tt(mag2), tt(ph1), tt(ph2)])
+        torch.mean(loss).backward()
+        np.savez_compressed(os.path.join(out_dir, f"phasegrad_{name}.npz"),
+                            **{"g:" + k: v.grad.detach().numpy().copy() for k, v in net.named_parameters()})
+        np.savez_compressed(os.path.join(out_dir, f"phase_{name}.npz"), cfg=np.array([B, T, F, H, L, D]), feature=feat,
+                            x_phase=x_phase, one_hot=oh, mag_mix=mix, mag_s1=mag1, mag_s2=mag2, phase_s1=ph1,
+                            phase_s2=ph2, emb=out[0].detach().numpy(), mask_a=out[1].detach().numpy(),
+                            mask_b=out[2].detach().numpy(), phase_a=out[3].detach().numpy(),
+                            phase_b=out[4].detach().numpy(), loss=loss.detach().numpy(),
+                            **{"p:" + k: v for k, v in sd.items()})
+        print("wrote phase", name)
+
+
 if __name__ == "__main__":
-    main()
+    # `--only phase` regenerates just the phase fixtures (the others are seeded independently and stay bit-identical)
+    if sys.argv[1:] != ["--only", "phase"]:
+        main()
+    main_phase()

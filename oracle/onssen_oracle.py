@@ -333,6 +333,12 @@ def loss_mask_psa(output, label):
     return _norm_1d(mask * noisy - np.minimum(noisy, np.maximum(clean * cosd, 0))).astype(F32)
 
 
+def loss_mask_psa_grad(mask, noisy, clean, cosd, g):
+    """d/dmask of sum_b g[b] * loss_mask_psa(...)[b] (onssen/loss/loss_mask.py:25-40): sign(residual) * noisy."""
+    res = mask * noisy - np.minimum(noisy, np.maximum(clean * cosd, 0))
+    return (np.sign(res) * noisy * g.reshape(-1, 1, 1)).astype(F32)
+
+
 def loss_phase(output, label):
     """REPAIRED restatement of onssen/loss/loss_phase.py:6-37 (no reference oracle).
     Repairs: assert 5 outputs (the reference asserts 6 then unpacks 5, :7,9); the embedding term is

@@ -107,3 +107,43 @@ def test_enhance_gradients_vs_reference(cuda_device, name):
         worst = max(worst, e)
         assert e < 3e-2, (k, e)
     print("enhance worst relative gradient error", worst)
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_phase_net_gradients_vs_torch_restatement(cuda_device, name):
+    """phase_net + loss_phase (both REPAIRED): forward and every parameter gradient against
+    the fixtures of the torch restatement with the same repairs (oracle/make_golden.py main_phase)."""
+    import onssen_b200 as ob
+    p, g = load_golden(f"phase_{name}.npz")
+    gz = np.load(f"tests/golden/phasegrad_{name}.npz")
+    B, T, F, H, L, D = [int(v) for v in g["cfg"]]
+    model = ob.nn.phase_net(F, H, L, D, dropout=0.0).to(cuda_device).train()
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()}, strict=False)
+    cu = lambda a: torch.from_numpy(a).to(cuda_device)
+    out = model([cu(g["feature"]), cu(g["x_phase"])])
+    for o, key in zip(out, ["emb", "mask_a", "mask_b", "phase_a", "phase_b"]):
+        assert np.abs(o.detach().cpu().numpy() - g[key]).max() < 3e-3, key
+    loss = ob.loss.loss_phase(out, [cu(g[k]) for k in ("one_hot", "mag_mix", "mag_s1", "mag_s2", "phase_s1", "phase_s2")])
+    assert np.allclose(loss.detach().cpu().numpy(), g["loss"], rtol=2e-3, atol=1e-2)
+    torch.mean(loss).backward()
+    worst = 0.0
+    for k, v in model.named_parameters():
+        e = rel_err(v.grad.cpu().numpy(), gz["g:" + k])
+        worst = max(worst, e)
+        assert e < 3e-2, (k, e)
+    print("phase_net worst relative gradient error", worst)
+
+
+def test_loss_mask_psa_gradient(cuda_device):
+    import onssen_b200 as ob
+    from oracle import onssen_oracle as O
+    _, g = load_golden("enhance_mid.npz")
+    rng = np.random.RandomState(3)
+    mask = rng.uniform(0, 1, g["mag_noisy"].shape).astype(np.float32)
+    cu = lambda a: torch.from_numpy(a).to(cuda_device)
+    m = cu(mask).requires_grad_(True)
+    loss = ob.loss.loss_mask_psa([m], [cu(g["mag_noisy"]), cu(g["mag_clean"]), cu(g["cos_diff"])])
+    w = rng.uniform(0.5, 2, loss.shape[0]).astype(np.float32)
+    (loss * cu(w)).sum().backward()
+    want = O.loss_mask_psa_grad(mask, g["mag_noisy"], g["mag_clean"], g["cos_diff"], w)
+    assert np.abs(m.grad.cpu().numpy() - want).max() < 1e-6

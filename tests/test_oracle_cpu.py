@@ -108,3 +108,17 @@ def test_oracle_loss_phase_repaired_runs():
     oh = np.zeros((B, T, F, 2)); oh[..., 0] = 1
     out = O.loss_phase([emb, ma, 1 - ma, ph(), ph()], [oh, mags[0], mags[1], mags[2], ph(), ph()])
     assert out.shape == (B, B) and np.isfinite(out).all()
+
+
+@pytest.mark.parametrize("name", ["small", "mid"])
+def test_oracle_phase_net_matches_torch_restatement(name):
+    """phase_net / loss_phase: numpy oracle vs the fixtures of the torch restatement with the same repairs
+    (oracle/make_golden.py main_phase; the reference itself raises -> parity unpinned for these rows)."""
+    p, g = load_golden(f"phase_{name}.npz")
+    B, T, F, H, L, D = [int(v) for v in g["cfg"]]
+    out = O.phase_net_forward(p, [g["feature"], g["x_phase"]], L, training=True)
+    for got, key in zip(out, ["emb", "mask_a", "mask_b", "phase_a", "phase_b"]):
+        assert np.abs(got - g[key]).max() < 2e-5, key
+    loss = O.loss_phase([g[k] for k in ("emb", "mask_a", "mask_b", "phase_a", "phase_b")],
+                        [g[k] for k in ("one_hot", "mag_mix", "mag_s1", "mag_s2", "phase_s1", "phase_s2")])
+    assert np.allclose(loss, g["loss"], rtol=2e-5, atol=1e-4)
