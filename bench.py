@@ -237,7 +237,7 @@ def run_gpu(args):
             loss = torch.mean(ob.loss.loss_dc(model(inp), lab))
             opt.zero_grad()
             loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+            ob.utils.clip_grad_norm_(model.parameters(), 5)
             opt.step()
             return loss
 

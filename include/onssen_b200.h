@@ -323,6 +323,19 @@ int onssen_phase_input_bwd(const float* d_xin, long long ld, const float* x_mag,
 int onssen_loss_l1_psa_bwd(const float* mask, const float* mag_noisy, const float* mag_clean, const float* cos_diff,
                            const float* g, int B, int N, float* d_mask, void* stream);
 
+/* ---- optimiser step (onssen/utils/train.py:83-84, onssen/utils/basic.py:6-7) ------------------------------------
+ * `tensors`: device array of records {float* param; float* grad; float* exp_avg; float* exp_avg_sq; int64 numel}
+ * (40 bytes each); `chunks`: device array of {int64 tensor_index; int64 start} (16 bytes), one per CUDA block,
+ * each covering chunk_elems consecutive elements of one tensor.
+ * onssen_clip_grad_norm = torch.nn.utils.clip_grad_norm_(params, max_norm): out2 = {total L2 norm, clip coefficient
+ * min(1, max_norm/(norm+1e-6))}; gradients are scaled in place only when the coefficient is < 1.  partials_f64:
+ * nchunks doubles of scratch.  No host synchronisation. */
+int onssen_clip_grad_norm(const void* tensors, const void* chunks, int nchunks, int chunk_elems, float max_norm,
+                          void* partials_f64, float* out2, void* stream);
+/* torch.optim.Adam.step (amsgrad off); `step` is the 1-based step count used for the bias corrections. */
+int onssen_adam_step(const void* tensors, const void* chunks, int nchunks, int chunk_elems, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, long long step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_bwd_set_persistent": (None, [c_int]),
     "onssen_blstm_rec_bwd_set_trace": (None, [c_vp]),
+    "onssen_clip_grad_norm": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
+    "onssen_adam_step": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_ll, c_vp]),
     "onssen_loss_l1_psa_bwd": (c_int, [c_vp] * 5 + [c_int] * 2 + [c_vp] * 2),
     "onssen_loss_phase_cos_bwd": (c_int, [c_vp] * 7 + [c_int] * 2 + [c_vp] * 3),
     "onssen_l2norm_pairs_bwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_vp] * 3),
@@ -668,3 +670,48 @@ def loss_l1_psa_bwd(mask, noisy, clean, cosd, g):
                                     _stream())
     _check(rc, "onssen_loss_l1_psa_bwd")
     return d_mask
+
+
+# ------------------------------------------------------------------------------------------------ optimiser step
+OPT_CHUNK = 65536
+
+
+class OptTables:
+    """Device tables for the multi-tensor optimiser kernels.  The chunk list only depends on the tensor sizes (built
+    once); the pointer records are rebuilt per call (gradient tensors are new objects after every backward)."""
+
+    def __init__(self, numels, device):
+        import numpy as np
+        self.numels = list(numels)
+        ch = [(i, s) for i, n in enumerate(self.numels) for s in range(0, n, OPT_CHUNK)]
+        self.nchunks = len(ch)
+        self.chunks = torch.from_numpy(np.array(ch, dtype=np.int64).reshape(-1, 2)).to(device)
+        self.partials = torch.empty(self.nchunks, device=device, dtype=torch.float64)
+        # pageable on purpose: the runtime stages a pageable source before cudaMemcpyAsync returns, so the buffer can be
+        # refilled for the next call while earlier copies are still queued (the loop never synchronises)
+        self.host = torch.empty(len(self.numels), 5, dtype=torch.int64)
+        self.dev = torch.empty(len(self.numels), 5, device=device, dtype=torch.int64)
+
+    def fill(self, rows):
+        """rows: iterable of (param_ptr, grad_ptr, m_ptr, v_ptr) ints; numel comes from the constructor."""
+        for i, r in enumerate(rows):
+            for j in range(4):
+                self.host[i, j] = r[j]
+            self.host[i, 4] = self.numels[i]
+        self.dev.copy_(self.host, non_blocking=True)
+        return self.dev
+
+
+def clip_grad_norm(tables, rows, max_norm, out2):
+    lib = load()
+    dev = tables.fill(rows)
+    _check(lib.onssen_clip_grad_norm(_p(dev), _p(tables.chunks), tables.nchunks, OPT_CHUNK, float(max_norm),
+                                     _p(tables.partials), _p(out2), _stream()), "onssen_clip_grad_norm")
+    return out2
+
+
+def adam_step(tables, rows, lr, beta1, beta2, eps, weight_decay, step):
+    lib = load()
+    dev = tables.fill(rows)
+    _check(lib.onssen_adam_step(_p(dev), _p(tables.chunks), tables.nchunks, OPT_CHUNK, float(lr), float(beta1),
+                                float(beta2), float(eps), float(weight_decay), int(step), _stream()), "onssen_adam_step")

@@ -25,6 +25,10 @@ def build_optimizer(params, optimizer_options):
     name = optimizer_options["name"]
     lr = optimizer_options["lr"]
     if name == "adam":
+        params = list(params)
+        if params and all(p.is_cuda for p in params):
+            from .optim import Adam          # multi-tensor kernel of libonssen_b200.so (csrc/optim.cu)
+            return Adam(params, lr=lr)
         return torch.optim.Adam(params, lr=lr)
     if name == "sgd":
         return torch.optim.SGD(params, lr=lr, momentum=0.9)

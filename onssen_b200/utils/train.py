@@ -11,6 +11,7 @@ import time
 import torch
 
 from .basic import AverageMeter
+from .optim import clip_grad_norm_
 
 
 class trainer:
@@ -65,7 +66,7 @@ class trainer:
             losses.update(loss_avg.item())
             self.optimizer.zero_grad()
             loss_avg.backward()
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), 5)
+            clip_grad_norm_(self.model.parameters(), 5)
             self.optimizer.step()
             times.update(time.time() - end)
             end = time.time()

@@ -364,6 +364,28 @@ def loss_phase(output, label):
 
 
 # ----------------------------------------------------------------------------------------------------
+# optimiser step  (onssen/utils/train.py:83-84, onssen/utils/basic.py:6-7)
+# ----------------------------------------------------------------------------------------------------
+def clip_adam_step(params, grads, exp_avg, exp_avg_sq, step, max_norm=5.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """torch.nn.utils.clip_grad_norm_(params, max_norm) then torch.optim.Adam(lr).step() [ext: torch semantics --
+    coefficient min(1, max_norm/(norm+1e-6)); bias-corrected moments, denom = sqrt(v)/sqrt(1-b2^t) + eps].
+    All arguments are lists of float32 arrays, updated in place; `step` is the 1-based step count.
+    Returns the total gradient norm."""
+    norm = np.sqrt(sum(float(np.sum(g.astype(np.float64) ** 2)) for g in grads))
+    coef = min(1.0, max_norm / (norm + 1e-6))
+    b1, b2 = betas
+    bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        if coef < 1.0:
+            g *= F32(coef)
+        m[...] = F32(b1) * m + F32(1 - b1) * g
+        v[...] = F32(b2) * v + F32(1 - b2) * g * g
+        denom = np.sqrt(v) / F32(np.sqrt(bc2)) + F32(eps)
+        p -= F32(lr / bc1) * (m / denom)
+    return norm
+
+
+# ----------------------------------------------------------------------------------------------------
 # synthetic workload shared by tests and bench (SURVEY.md section 8d)
 # ----------------------------------------------------------------------------------------------------
 def synth_utterance(index, nsample=32000, seed0=1234):

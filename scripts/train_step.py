@@ -15,5 +15,5 @@ for it in range(int(os.environ.get("STEPS", 2))):
     inp, lab = ob.data.featurize_batch(ws[0], ws[1], ws[2], "dc", C["n_fft"], C["hop"], C["T"], C["db"], crop_start=st)
     loss = torch.mean(ob.loss.loss_dc(model(inp), lab))
     opt.zero_grad(); loss.backward()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), 5); opt.step()
+    ob.utils.clip_grad_norm_(model.parameters(), 5); opt.step()
 torch.cuda.synchronize(); print("loss", loss.item())

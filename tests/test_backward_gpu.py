@@ -64,7 +64,7 @@ def test_training_step_reduces_loss(cuda_device):
         loss = torch.mean(ob.loss.loss_dc(model(inp), lab))
         opt.zero_grad()
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+        ob.utils.clip_grad_norm_(model.parameters(), 5)
         opt.step()
         losses.append(loss.item())
     assert np.isfinite(losses).all() and losses[-1] < 0.9 * losses[0], losses
@@ -147,3 +147,29 @@ def test_loss_mask_psa_gradient(cuda_device):
     (loss * cu(w)).sum().backward()
     want = O.loss_mask_psa_grad(mask, g["mag_noisy"], g["mag_clean"], g["cos_diff"], w)
     assert np.abs(m.grad.cpu().numpy() - want).max() < 1e-6
+
+
+def test_clip_grad_norm_and_adam_kernels_vs_oracle(cuda_device):
+    """multi-tensor clip_grad_norm_ + Adam (csrc/optim.cu) against the oracle restatement, clipping and not clipping"""
+    import onssen_b200 as ob
+    from oracle import onssen_oracle as O
+    rng = np.random.RandomState(9)
+    shapes = [(2400, 129), (70001,), (5, 3, 7), (1,), (65536,), (65537,)]
+    ps = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    tp = [torch.nn.Parameter(torch.from_numpy(p.copy()).to(cuda_device)) for p in ps]
+    opt = ob.utils.build_optimizer(tp, {"name": "adam", "lr": 1e-3})
+    assert isinstance(opt, ob.utils.Adam)
+    m = [np.zeros_like(p) for p in ps]
+    v = [np.zeros_like(p) for p in ps]
+    for step in range(1, 5):
+        gs = [(rng.standard_normal(s) * (1.0 if step % 2 else 1e-3)).astype(np.float32) for s in shapes]
+        for t, g in zip(tp, gs):
+            t.grad = torch.from_numpy(g.copy()).to(cuda_device)
+        ver = tp[0]._version
+        tn = float(ob.utils.clip_grad_norm_(tp, 5))
+        opt.step()
+        assert tp[0]._version > ver
+        n = O.clip_adam_step(ps, [g.copy() for g in gs], m, v, step)
+        assert abs(n - tn) < 1e-5 * max(n, 1e-3), (n, tn)
+        for a, t in zip(ps, tp):
+            assert np.abs(a - t.detach().cpu().numpy()).max() < 2e-6

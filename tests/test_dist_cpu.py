@@ -123,3 +123,36 @@ def test_edinburgh_loader_file_conventions(tmp_path):
     (mix, clean, noise), lengths = ld._load(sorted(ld.file_list)[:2])
     assert mix.shape == (2, 3010) and lengths.tolist() == [3000, 3010]
     assert torch.allclose(mix - clean, noise, atol=1e-6)       # "speaker 2" = mix - clean
+
+
+def test_daps_segment_cursor_semantics(tmp_path):
+    """daps_enhance.py:90-122: consecutive non-overlapping segments of the current recording; a new file is popped at
+    index % len(list) when fewer than frame_length frames remain; the list is re-read when exhausted."""
+    import random
+    from onssen_b200.data.daps_enhance import SegmentCursor, daps_enhance_dataloader
+    lengths = {"a_x_noisy.wav": 25, "b_y_noisy.wav": 10, "c_z_noisy.wav": 31}
+    (tmp_path / "train").write_text("\n".join(lengths) + "\n")
+    calls = []
+
+    def featurize(path):
+        calls.append(path)
+        n = lengths[path]
+        base = torch.arange(n, dtype=torch.float32)[:, None] + 1000 * len(calls)
+        return [base, base + 0.5], [base + 0.25, base + 0.75]
+
+    random.seed(0)
+    cur = SegmentCursor(str(tmp_path / "train"), 10, featurize)
+    segs = [cur.next_item(i) for i in (5, 1, 7, 2, 9, 4, 0)]
+    firsts = [float(s[0][0][0, 0]) for s in segs]
+    # every item is 10 frames; segments of one file are consecutive and leftovers (< 10 frames) are dropped
+    assert all(s[0][0].shape == (10, 1) and s[1][1].shape == (10, 1) for s in segs)
+    per_file = {}
+    for f in firsts:
+        per_file.setdefault(int(f // 1000), []).append(f % 1000)
+    assert all(v == [10.0 * i for i in range(len(v))] for v in per_file.values())
+    counts = [len(per_file[k]) for k in sorted(per_file)]
+    assert counts[:-1] == [lengths[c] // 10 for c in calls][:len(counts) - 1] and sum(counts) == 7
+    assert len(calls) >= 4 and set(calls[:3]) == set(lengths)      # list exhausted -> re-read (file 4 = a repeat)
+    ld = daps_enhance_dataloader(3, dict(data_path=str(tmp_path), batch_size=2, frame_length=10, sampling_rate=16000,
+                                         window_size=512, hop_size=128), "train")
+    assert len(ld) == 3 and ld.clean_path("/x/f1_script2_iphone.wav") == str(tmp_path) + "/clean/f1_script2_clean.wav"

@@ -122,3 +122,25 @@ def test_oracle_phase_net_matches_torch_restatement(name):
     loss = O.loss_phase([g[k] for k in ("emb", "mask_a", "mask_b", "phase_a", "phase_b")],
                         [g[k] for k in ("one_hot", "mag_mix", "mag_s1", "mag_s2", "phase_s1", "phase_s2")])
     assert np.allclose(loss, g["loss"], rtol=2e-5, atol=1e-4)
+
+
+def test_oracle_clip_adam_matches_torch():
+    """the optimiser restatement against the reference's actual implementation (torch clip_grad_norm_ + optim.Adam)"""
+    import torch
+    rng = np.random.RandomState(5)
+    shapes = [(7, 5), (33,), (4, 3, 2), (1,)]
+    ps = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    tp = [torch.nn.Parameter(torch.from_numpy(p.copy())) for p in ps]
+    opt = torch.optim.Adam(tp, lr=1e-3)
+    m = [np.zeros_like(p) for p in ps]
+    v = [np.zeros_like(p) for p in ps]
+    for step in range(1, 5):
+        gs = [(rng.standard_normal(s) * (3.0 if step % 2 else 0.1)).astype(np.float32) for s in shapes]
+        for t, g in zip(tp, gs):
+            t.grad = torch.from_numpy(g.copy())
+        tn = float(torch.nn.utils.clip_grad_norm_(tp, 5))
+        opt.step()
+        n = O.clip_adam_step(ps, [g.copy() for g in gs], m, v, step)
+        assert abs(n - tn) < 1e-4 * tn
+        for a, t in zip(ps, tp):
+            assert np.abs(a - t.detach().numpy()).max() < 2e-6

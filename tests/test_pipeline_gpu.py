@@ -96,3 +96,47 @@ def test_device_prefetcher_matches_inline_featurizer(cuda_device):
         torch.cuda.synchronize()
         for a, b in zip(inp + lab, ri + rl):
             assert torch.equal(a, b)
+
+
+def test_daps_loader_segments_match_oracle(cuda_device, tmp_path):
+    """daps_enhance loader: a whole recording featurized on the device, consecutive frame_length segments, batched;
+    every item must equal the oracle's features of the same recording at the same frames."""
+    import random
+    from scipy.io import wavfile
+    import onssen_b200 as ob
+    os.makedirs(tmp_path / "clean", exist_ok=True)
+    os.makedirs(tmp_path / "noisy", exist_ok=True)
+    q = lambda x: np.clip(np.round(x * 32768), -32768, 32767).astype(np.int16)
+    recs, lines = {}, []
+    for i in range(2):
+        ns = 16000 + 1280 * i
+        mix, s1, _ = O.synth_utterance(40 + i, ns)
+        fn = str(tmp_path / "noisy" / f"f{i}_script{i}_ipad.wav")
+        wavfile.write(fn, 16000, q(mix))
+        wavfile.write(str(tmp_path / "clean" / f"f{i}_script{i}_clean.wav"), 16000, q(s1))
+        recs[fn] = (q(mix).astype(np.float32) / 32768, q(s1).astype(np.float32) / 32768)
+        lines.append(fn)
+    (tmp_path / "train").write_text("\n".join(lines) + "\n")
+    T, n_fft, hop = 50, 512, 128
+    fo = dict(data_path=str(tmp_path), batch_size=2, frame_length=T, sampling_rate=16000, window_size=n_fft, hop_size=hop)
+    random.seed(3)
+    ld = ob.data.daps_enhance_dataloader(2, fo, "train", cuda_device)
+    order = []
+    orig = ld.cursor.featurize
+    ld.cursor.featurize = lambda p: (order.append(p), orig(p))[1]
+    batches = list(ld)
+    assert len(batches) == 2 and batches[0][0][0].shape == (2, T, n_fft // 2 + 1)
+    items = [(b[0][0][k], b[0][1][k], b[1][0][k], b[1][1][k]) for b in batches for k in range(2)]
+    # 1 + 16000/128 = 126 frames -> 2 segments per recording, then the next file
+    want = []
+    for fn in order:
+        noisy, clean = recs[fn]
+        sn, sc = O.stft(noisy, n_fft, hop), O.stft(clean, n_fft, hop)
+        for k in range(sn.shape[0] // T):
+            sl = slice(k * T, (k + 1) * T)
+            want.append((O.log_magnitude(sn)[sl], np.abs(sn)[sl], np.abs(sc)[sl], O.cos_difference(sn, sc)[sl], np.abs(sc)[sl]))
+    for got, w in zip(items, want):
+        assert np.abs(got[0].cpu().numpy() - w[0]).max() < 2e-3
+        assert np.abs(got[1].cpu().numpy() - w[1]).max() < 1e-4
+        assert np.abs(got[2].cpu().numpy() - w[2]).max() < 1e-4
+        assert (np.abs(got[3].cpu().numpy() - w[3]) * w[4]).max() < 2e-4   # cos is ill-conditioned on tiny bins
