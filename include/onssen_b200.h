@@ -336,6 +336,22 @@ int onssen_clip_grad_norm(const void* tensors, const void* chunks, int nchunks, 
 int onssen_adam_step(const void* tensors, const void* chunks, int nchunks, int chunk_elems, float lr, float beta1,
                      float beta2, float eps, float weight_decay, long long step, void* stream);
 
+/* ---- BatchNorm with cross-rank batch statistics (per-replica statistics differ from the
+ * single-device maths of deep_clustering.py:36-38; this is the parity mode).  Forward: onssen_bn_stats writes this
+ * rank's column sums and sums of squares as 2*2Hp doubles; the caller all-reduces them (SUM) and calls
+ * onssen_bn_forward_f16_stats with M_total = rows over all ranks.  Backward likewise: onssen_bn_backward_stats ->
+ * all-reduce -> onssen_bn_backward_apply (d_gamma / d_beta stay this rank's local sums, as data-parallel gradient
+ * averaging expects; the SAME scratch buffer must be passed to both backward calls). */
+int onssen_bn_stats(const float* y, int M, int H, void* sums_f64, void* scratch, void* stream);
+int onssen_bn_forward_f16_stats(const float* y, int M, int M_total, int H, const void* sums_f64, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                                void* out_h, float* save_mean, float* save_invstd, void* scratch, void* stream);
+int onssen_bn_backward_stats(const float* d_out, const float* y, int M, int H, const float* save_mean,
+                             const float* save_invstd, void* sums_f64, void* scratch, void* stream);
+int onssen_bn_backward_apply(const float* d_out, const float* y, int M, int M_total, int H, const float* gamma,
+                             const float* save_mean, const float* save_invstd, const void* sums_total_f64, float* d_y,
+                             float* d_gamma, float* d_beta, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

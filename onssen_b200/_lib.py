@@ -67,6 +67,11 @@ _SIGNATURES = {
     "onssen_blstm_rec_bwd_set_trace": (None, [c_vp]),
     "onssen_clip_grad_norm": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "onssen_adam_step": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_ll, c_vp]),
+    "onssen_bn_stats": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_bn_forward_f16_stats": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp,
+                                            c_vp, c_vp, c_vp]),
+    "onssen_bn_backward_stats": (c_int, [c_vp, c_vp, c_int, c_int] + [c_vp] * 5),
+    "onssen_bn_backward_apply": (c_int, [c_vp, c_vp, c_int, c_int, c_int] + [c_vp] * 9),
     "onssen_loss_l1_psa_bwd": (c_int, [c_vp] * 5 + [c_int] * 2 + [c_vp] * 2),
     "onssen_loss_phase_cos_bwd": (c_int, [c_vp] * 7 + [c_int] * 2 + [c_vp] * 3),
     "onssen_l2norm_pairs_bwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_vp] * 3),
@@ -295,7 +300,10 @@ def blstm_rec_fwd(gates, whh_p, B, T, H, y_h=None, y_f=None, dropout_p=0.0, seed
     _check(rc, "onssen_blstm_rec_fwd")
 
 
-def bn_forward_f16(y, M, H, gamma, beta, running_mean, running_var, eps, momentum, training, save_stats=False):
+def bn_forward_f16(y, M, H, gamma, beta, running_mean, running_var, eps, momentum, training, save_stats=False,
+                   sync=None):
+    """sync = (all_reduce_sum(tensor) -> None, world_size) switches train-mode statistics to the whole data-parallel
+    batch (equal shards assumed: M_total = M * world_size)."""
     lib = load()
     Hp = hp_of(H)
     out_h = torch.empty(M, 2 * Hp, device=y.device, dtype=torch.float16)
@@ -304,6 +312,17 @@ def bn_forward_f16(y, M, H, gamma, beta, running_mean, running_var, eps, momentu
     if save_stats:
         sm = torch.empty(2 * H, device=y.device, dtype=torch.float32)
         si = torch.empty(2 * H, device=y.device, dtype=torch.float32)
+    if sync is not None and training:
+        reduce_sum, world = sync
+        sums = torch.empty(2 * 2 * Hp, device=y.device, dtype=torch.float64)
+        _check(lib.onssen_bn_stats(_p(_req(y, torch.float32, "y")), M, H, _p(sums), _p(scratch), _stream()),
+               "onssen_bn_stats")
+        reduce_sum(sums)
+        rc = lib.onssen_bn_forward_f16_stats(_p(y), M, M * world, H, _p(sums), _p(gamma), _p(beta), _p(running_mean),
+                                             _p(running_var), float(eps), float(momentum), _p(out_h), _p(sm), _p(si),
+                                             _p(scratch), _stream())
+        _check(rc, "onssen_bn_forward_f16_stats")
+        return out_h, sm, si
     rc = lib.onssen_bn_forward_f16(_p(_req(y, torch.float32, "y")), M, H, _p(gamma), _p(beta), _p(running_mean),
                                    _p(running_var), float(eps), float(momentum), int(training), _p(out_h), _p(sm),
                                    _p(si), _p(scratch), _stream())
@@ -502,12 +521,23 @@ def normalize_bwd(d_emb, emb, inv_norm):
     return dz, scale2
 
 
-def bn_backward(d_out, y, M, H, gamma, save_mean, save_invstd):
+def bn_backward(d_out, y, M, H, gamma, save_mean, save_invstd, sync=None):
     lib = load()
     d_y = torch.empty_like(y)
     dg = torch.empty(2 * H, device=y.device, dtype=torch.float32)
     db = torch.empty(2 * H, device=y.device, dtype=torch.float32)
     scratch = torch.empty(lib.onssen_bn_backward_scratch_bytes(M, H), device=y.device, dtype=torch.uint8)
+    if sync is not None:
+        reduce_sum, world = sync
+        sums = torch.empty(2 * 2 * hp_of(H), device=y.device, dtype=torch.float64)
+        _check(lib.onssen_bn_backward_stats(_p(_req(d_out, torch.float32)), _p(_req(y, torch.float32)), M, H,
+                                            _p(save_mean), _p(save_invstd), _p(sums), _p(scratch), _stream()),
+               "onssen_bn_backward_stats")
+        reduce_sum(sums)
+        rc = lib.onssen_bn_backward_apply(_p(d_out), _p(y), M, M * world, H, _p(gamma), _p(save_mean), _p(save_invstd),
+                                          _p(sums), _p(d_y), _p(dg), _p(db), _p(scratch), _stream())
+        _check(rc, "onssen_bn_backward_apply")
+        return d_y, dg, db
     rc = lib.onssen_bn_backward(_p(_req(d_out, torch.float32)), _p(_req(y, torch.float32)), M, H, _p(gamma),
                                 _p(save_mean), _p(save_invstd), _p(d_y), _p(dg), _p(db), _p(scratch), _stream())
     _check(rc, "onssen_bn_backward")

@@ -179,10 +179,13 @@ bn_bwd_partial_kernel(const float* __restrict__ d_out, const float* __restrict__
     part[(long long)(nchunk + blockIdx.y) * C + c] = t1;
   }
 }
-__global__ void bn_bwd_final_kernel(const double* __restrict__ part, int nchunk, int M, int H, int Hp,
-                                    const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                    float* __restrict__ d_gamma, float* __restrict__ d_beta,
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, int nchunk, const double* __restrict__ total,
+                                    int M_total, int H, int Hp, const float* __restrict__ gamma,
+                                    const float* __restrict__ invstd, float* __restrict__ d_gamma,
+                                    float* __restrict__ d_beta,
                                     float* __restrict__ coef /* [3][C]: a, b, c of dy = a*g + b*yhat + c */) {
+  // part: this rank's per-chunk sums (-> d_gamma, d_beta); total (nullable): sums over ALL ranks [2][C] used with
+  // M_total for the input gradient (cross-rank batch statistics); without it the local sums are the totals
   const int C = 2 * Hp;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -196,10 +199,14 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ part, int nchunk,
   }
   d_beta[j] = (float)sg;
   d_gamma[j] = (float)sgy;
+  if (total != nullptr) {
+    sg = total[c];
+    sgy = total[C + c];
+  }
   const float a = gamma[j] * invstd[j];
   coef[c] = a;
-  coef[C + c] = -a * (float)(sgy / M);
-  coef[2 * C + c] = -a * (float)(sg / M);
+  coef[C + c] = -a * (float)(sgy / M_total);
+  coef[2 * C + c] = -a * (float)(sg / M_total);
 }
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ d_out, const float* __restrict__ y, long long M, int H,
                                     int Hp, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -597,8 +604,50 @@ extern "C" int onssen_bn_backward(const float* d_out, const float* y, int M, int
   float* coef = (float*)(part + 2LL * nchunk * C);
   cudaStream_t s = (cudaStream_t)stream;
   bn_bwd_partial_kernel<<<dim3((C + 31) / 32, nchunk), 256, 0, s>>>(d_out, y, M, H, Hp, save_mean, save_invstd, part);
-  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, nchunk, M, H, Hp, gamma, save_invstd, d_gamma, d_beta,
-                                                      coef);
+  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, nchunk, nullptr, M, H, Hp, gamma, save_invstd, d_gamma,
+                                                      d_beta, coef);
+  bn_bwd_apply_kernel<<<grid_for((long long)M * C, 256), 256, 0, s>>>(d_out, y, M, H, Hp, save_mean, save_invstd,
+                                                                      coef, d_y);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+// cross-rank variant: onssen_bn_backward_stats -> [caller all-reduces 2*C doubles] -> onssen_bn_backward_apply
+__global__ void bwd_chunk_sum_kernel(const double* __restrict__ part, int nchunk, int C2, double* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C2) return;
+  const int C = C2 / 2;
+  const int half = c / C, col = c % C;
+  double t = 0.0;
+  for (int k = 0; k < nchunk; ++k) t += part[(long long)(half * nchunk + k) * C + col];
+  sums[c] = t;
+}
+
+extern "C" int onssen_bn_backward_stats(const float* d_out, const float* y, int M, int H, const float* save_mean,
+                                        const float* save_invstd, void* sums_f64, void* scratch, void* stream) {
+  if (!d_out || !y || !save_mean || !save_invstd || !sums_f64 || !scratch || M <= 0 || H <= 0) return ONSSEN_ERR_ARG;
+  const int Hp = hp_of(H), C = 2 * Hp;
+  const int nchunk = (M + CS_ROWS - 1) / CS_ROWS;
+  cudaStream_t s = (cudaStream_t)stream;
+  bn_bwd_partial_kernel<<<dim3((C + 31) / 32, nchunk), 256, 0, s>>>(d_out, y, M, H, Hp, save_mean, save_invstd,
+                                                                    (double*)scratch);
+  bwd_chunk_sum_kernel<<<(2 * C + 127) / 128, 128, 0, s>>>((const double*)scratch, nchunk, 2 * C, (double*)sums_f64);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_bn_backward_apply(const float* d_out, const float* y, int M, int M_total, int H,
+                                        const float* gamma, const float* save_mean, const float* save_invstd,
+                                        const void* sums_total_f64, float* d_y, float* d_gamma, float* d_beta,
+                                        void* scratch, void* stream) {
+  if (!d_out || !y || !gamma || !save_mean || !save_invstd || !sums_total_f64 || !d_y || !d_gamma || !d_beta ||
+      !scratch || M <= 0 || M_total < M)
+    return ONSSEN_ERR_ARG;
+  const int Hp = hp_of(H), C = 2 * Hp;
+  const int nchunk = (M + CS_ROWS - 1) / CS_ROWS;
+  double* part = (double*)scratch;           // still holds this rank's per-chunk sums from onssen_bn_backward_stats
+  float* coef = (float*)(part + 2LL * nchunk * C);
+  cudaStream_t s = (cudaStream_t)stream;
+  bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, nchunk, (const double*)sums_total_f64, M_total, H, Hp,
+                                                      gamma, save_invstd, d_gamma, d_beta, coef);
   bn_bwd_apply_kernel<<<grid_for((long long)M * C, 256), 256, 0, s>>>(d_out, y, M, H, Hp, save_mean, save_invstd,
                                                                       coef, d_y);
   return ONSSEN_CHECK_LAUNCH();

@@ -309,6 +309,48 @@ extern "C" int onssen_bn_forward_f16(const float* y, int M, int H, const float* 
   return ONSSEN_CHECK_LAUNCH();
 }
 
+// ---- cross-rank (SyncBN-style) batch statistics: local sums -> [caller all-reduces 2*C doubles] -> apply ----------
+namespace onssen { namespace {
+__global__ void chunk_sum_kernel(const double* __restrict__ part, int nchunk, int C2, double* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*C (sum rows then square rows)
+  if (c >= C2) return;
+  const int C = C2 / 2;
+  const int half = c / C, col = c % C;
+  double t = 0.0;
+  for (int k = 0; k < nchunk; ++k) t += part[(long long)(half * nchunk + k) * C + col];
+  sums[c] = t;
+}
+} }
+
+extern "C" int onssen_bn_stats(const float* y, int M, int H, void* sums_f64, void* scratch, void* stream) {
+  if (!y || !sums_f64 || !scratch || M <= 0 || H <= 0) return ONSSEN_ERR_ARG;
+  const int C = 2 * hp_of(H);
+  const int nchunk = onssen_bn_num_chunks(M);
+  cudaStream_t s = (cudaStream_t)stream;
+  bn_partial_kernel<<<dim3((C + 31) / 32, nchunk), 256, 0, s>>>(y, M, C, (double*)scratch);
+  chunk_sum_kernel<<<(2 * C + 127) / 128, 128, 0, s>>>((const double*)scratch, nchunk, 2 * C, (double*)sums_f64);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
+extern "C" int onssen_bn_forward_f16_stats(const float* y, int M, int M_total, int H, const void* sums_f64,
+                                           const float* gamma, const float* beta, float* running_mean,
+                                           float* running_var, float eps, float momentum, void* out_h,
+                                           float* save_mean, float* save_invstd, void* scratch, void* stream) {
+  if (!y || !sums_f64 || !gamma || !beta || !running_mean || !running_var || !out_h || !scratch || M <= 0 ||
+      M_total < M || H <= 0)
+    return ONSSEN_ERR_ARG;
+  const int Hp = hp_of(H);
+  const int C = 2 * Hp;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* scale = (float*)((double*)scratch + 2LL * onssen_bn_num_chunks(M) * C);
+  float* shift = scale + C;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>((const double*)sums_f64, 1, M_total, H, Hp, gamma, beta,
+                                                     running_mean, running_var, eps, momentum, 1, scale, shift,
+                                                     save_mean, save_invstd);
+  bn_apply_f16_kernel<<<grid_for((long long)M * C / 4, 256), 256, 0, s>>>(y, M, C, scale, shift, (__half*)out_h);
+  return ONSSEN_CHECK_LAUNCH();
+}
+
 extern "C" int onssen_cast_f16(const float* y, long long n, void* out_h, void* stream) {
   if (!y || !out_h || n <= 0 || (n & 3)) return ONSSEN_ERR_ARG;
   cast_f16_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(y, n / 4, (__half*)out_h);

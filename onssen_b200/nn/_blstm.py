@@ -56,6 +56,19 @@ def pack_lstm(rnn):
     return packed
 
 
+def bn_sync(model):
+    """(all_reduce_sum, world_size) when `model.sync_bn` is set and a process group with more than one rank is up
+    (utils.ddp.enable_sync_batchnorm), else None: train-mode BatchNorm statistics then cover the whole
+    data-parallel batch, which is the single-device arithmetic of deep_clustering.py:36-38."""
+    import torch.distributed as dist
+    if not getattr(model, "sync_bn", False) or not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size()
+    if world == 1:
+        return None
+    return (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)), world
+
+
 def require_no_grad(module_name, *tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(

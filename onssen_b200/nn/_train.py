@@ -8,7 +8,7 @@ gradients (tcgen05 GEMMs contracting over all (t,b)) + dgrad to the layer below.
 import torch
 
 from .. import _lib
-from ._blstm import _next_seed, lstm_layer_params, pack_lstm
+from ._blstm import _next_seed, bn_sync, lstm_layer_params, pack_lstm
 
 
 # ------------------------------------------------------------------------------------------------ shared pieces
@@ -147,7 +147,7 @@ def dc_forward_train(model, x):
     M = T * B
     layers, packed, y_f = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=True)
     a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True)
+                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True, sync=bn_sync(model))
     bn.num_batches_tracked += 1
     w_p = model._fc_cache.get([model.fc_dc.weight], lambda: _lib.pack_linear_f16(model.fc_dc.weight, True, H))
     emb = torch.empty(B, T, F, D, device=x.device, dtype=torch.float32)
@@ -172,7 +172,7 @@ def dc_backward(model, saved, d_outs, on_grads=None):
     dA = linear_backward(dz32, sc, saved["a_h"], saved["w_p"], N, H, grads, "fc_dc")
     del dz32
     dY, grads["bn.weight"], grads["bn.bias"] = _lib.bn_backward(dA, saved["y_f"], M, H, bn.weight.detach(),
-                                                                saved["mean"], saved["invstd"])
+                                                                saved["mean"], saved["invstd"], sync=bn_sync(model))
     if on_grads is not None:
         on_grads(dict(grads))
     return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)
@@ -239,7 +239,7 @@ def enhance_forward_train(model, x_and_noisy):
     dev = x.device
     layers, packed, y_f = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=True)
     a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True)
+                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True, sync=bn_sync(model))
     bn.num_batches_tracked += 1
     w_mi = model._mi.get([model.fc_mi.weight], lambda: _lib.pack_linear_f16(model.fc_mi.weight, True, H))
     w_pre = model._pre.get([model.fc_pre.weight], lambda: _lib.pack_linear_f16(model.fc_pre.weight, False))
@@ -271,7 +271,7 @@ def enhance_backward(model, saved, d_outs, on_grads=None):
     linear_backward(dz_pre, sc_pre, saved["noisy_h"], saved["w_pre"], F, H, grads, "fc_pre", K=F, want_dA=False)
     dA = linear_backward(dz_mi, sc_mi, saved["a_h"], saved["w_mi"], F, H, grads, "fc_mi")
     dY, grads["bn.weight"], grads["bn.bias"] = _lib.bn_backward(dA, saved["y_f"], M, H, bn.weight.detach(),
-                                                                saved["mean"], saved["invstd"])
+                                                                saved["mean"], saved["invstd"], sync=bn_sync(model))
     if on_grads is not None:
         on_grads(dict(grads))
     return blstm_backward(rnn, saved["layers"], saved["packed"], dY, B, T, grads, "rnn.", on_grads)
@@ -293,7 +293,7 @@ def phase_forward_train(model, inp):
         xin = _lib.pack_phase_input_f16(x_mag, mk, mk.stride(-1), x_phase)
         layers, packed, y_f = blstm_forward_train_packed(model.rnn, model._rnn_cache, xin, B, T, model.training, True)
         a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                                bn.running_var, bn.eps, bn.momentum, True, save_stats=True)
+                                                bn.running_var, bn.eps, bn.momentum, True, save_stats=True, sync=bn_sync(model))
         bn.num_batches_tracked += 1
         ph = torch.empty(B, T, F, 2, device=x_mag.device, dtype=torch.float32)
         _lib.gemm_f16(a_h, w_ph, model.fc_phase.bias.detach(), ph, M, 2 * F, a_h.shape[1], 2 * F, remap_inner=B,
@@ -322,7 +322,7 @@ def phase_backward(model, saved, d_outs, on_grads=None):
         dz, sc = _lib.l2norm_pairs_bwd(d_p, br["ph"], saved["x_phase"])
         dA = linear_backward(dz, sc, br["a_h"], saved["w_ph"], 2 * F, H, g, "fc_phase")
         dY, g["bn.weight"], g["bn.bias"] = _lib.bn_backward(dA, br["y_f"], M, H, bn.weight.detach(), br["mean"],
-                                                            br["invstd"])
+                                                            br["invstd"], sync=bn_sync(model))
         g, d_xin = blstm_backward(model.rnn, br["layers"], br["packed"], dY, B, T, g, "rnn.", None, want_dx0=True)
         _lib.phase_input_bwd(d_xin, saved["x_mag"], d_masks, s_idx)
         if total is None:

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward
+from ._blstm import PackCache, blstm_forward, bn_sync
 
 
 class deep_clustering(nn.Module):
@@ -38,7 +38,7 @@ class deep_clustering(nn.Module):
                                use_tensor_cores=self.use_tensor_cores)
         bn = self.bn
         a_h, _, _ = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                        bn.running_var, bn.eps, bn.momentum, self.training)
+                                        bn.running_var, bn.eps, bn.momentum, self.training, sync=bn_sync(self))
         if self.training:
             bn.num_batches_tracked += 1
         w_p = self._fc_cache.get([self.fc_dc.weight], lambda: _lib.pack_linear_f16(self.fc_dc.weight, True, H))

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward
+from ._blstm import PackCache, blstm_forward, bn_sync
 
 
 class enhance(nn.Module):
@@ -39,7 +39,7 @@ class enhance(nn.Module):
                                use_tensor_cores=self.use_tensor_cores)
         bn = self.bn
         a_h, _, _ = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                        bn.running_var, bn.eps, bn.momentum, self.training)
+                                        bn.running_var, bn.eps, bn.momentum, self.training, sync=bn_sync(self))
         if self.training:
             bn.num_batches_tracked += 1
         w_mi = self._mi.get([self.fc_mi.weight], lambda: _lib.pack_linear_f16(self.fc_mi.weight, True, H))

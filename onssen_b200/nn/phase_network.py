@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache
+from ._blstm import PackCache, bn_sync
 from .chimera import chimera
 
 
@@ -33,7 +33,7 @@ class phase_net(nn.Module):
         _, y_f = blstm_forward_packed(self.rnn, self._rnn_cache, xin_h, B, T, self.training, True, False)
         bn = self.bn
         a_h, _, _ = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                        bn.running_var, bn.eps, bn.momentum, self.training)
+                                        bn.running_var, bn.eps, bn.momentum, self.training, sync=bn_sync(self))
         if self.training:
             bn.num_batches_tracked += 1
         w = self._ph.get([self.fc_phase.weight], lambda: _lib.pack_linear_f16(self.fc_phase.weight, True, H))

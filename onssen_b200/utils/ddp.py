@@ -47,3 +47,14 @@ def broadcast_parameters(model, src=0):
         return
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
+
+
+def enable_sync_batchnorm(model, on=True):
+    """Train-mode BatchNorm statistics (and their backward) over the WHOLE data-parallel batch: one all-reduce of
+    2 x 2Hp doubles per BatchNorm call, forward and backward.  Without it each rank normalises with its own shard's
+    statistics, which differs from the single-device arithmetic of deep_clustering.py:36-38.
+    Equal per-rank batch sizes are assumed."""
+    for m in model.modules():
+        if hasattr(m, "bn"):
+            m.sync_bn = bool(on)
+    return model

@@ -162,11 +162,13 @@ def main_phase():
             x_mag, x_phase = inp
             emb, m_a, m_b = self.chimera([x_mag])
             B, T, F = m_a.shape
-            outs = []
+            outs, self.pre_norms = [], []
             for m in (m_a, m_b):
                 y, _ = self.rnn(torch.cat((x_mag * m, x_phase.reshape(B, T, -1)), 2))
                 y = self.bn(y.permute(0, 2, 1)).permute(0, 2, 1)
-                outs.append(Fn.normalize(self.fc_phase(y).reshape(B, T, F, -1) + x_phase, p=2, dim=-1))
+                v = self.fc_phase(y).reshape(B, T, F, -1) + x_phase
+                self.pre_norms.append(v.detach().norm(dim=-1))   # conditioning of the normalisation, for the tests
+                outs.append(Fn.normalize(v, p=2, dim=-1))
             return [emb, m_a, m_b] + outs
 
     def loss_phase_repaired(output, label):
@@ -205,6 +207,7 @@ def main_phase():
                             phase_s2=ph2, emb=out[0].detach().numpy(), mask_a=out[1].detach().numpy(),
                             mask_b=out[2].detach().numpy(), phase_a=out[3].detach().numpy(),
                             phase_b=out[4].detach().numpy(), loss=loss.detach().numpy(),
+                            norm_a=net.pre_norms[0].numpy(), norm_b=net.pre_norms[1].numpy(),
                             **{"p:" + k: v for k, v in sd.items()})
         print("wrote phase", name)
 

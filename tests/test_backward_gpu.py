@@ -121,8 +121,12 @@ def test_phase_net_gradients_vs_torch_restatement(cuda_device, name):
     model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()}, strict=False)
     cu = lambda a: torch.from_numpy(a).to(cuda_device)
     out = model([cu(g["feature"]), cu(g["x_phase"])])
-    for o, key in zip(out, ["emb", "mask_a", "mask_b", "phase_a", "phase_b"]):
-        assert np.abs(o.detach().cpu().numpy() - g[key]).max() < 3e-3, key
+    # the (re,im) normalisation amplifies errors by 1/|v| where the pre-normalisation vector is short (x_phase is a raw
+    # STFT, so it is on quiet bins): weight the phase error by min(1, |v|) of the restatement
+    one = np.ones(g["mask_a"].shape, np.float32)
+    for o, key, w in zip(out, ["emb", "mask_a", "mask_b", "phase_a", "phase_b"],
+                         [one[..., None], one, one, np.minimum(1, g["norm_a"])[..., None], np.minimum(1, g["norm_b"])[..., None]]):
+        assert (np.abs(o.detach().cpu().numpy() - g[key]) * w).max() < 3e-3, key
     loss = ob.loss.loss_phase(out, [cu(g[k]) for k in ("one_hot", "mag_mix", "mag_s1", "mag_s2", "phase_s1", "phase_s2")])
     assert np.allclose(loss.detach().cpu().numpy(), g["loss"], rtol=2e-3, atol=1e-2)
     torch.mean(loss).backward()
@@ -173,3 +177,41 @@ def test_clip_grad_norm_and_adam_kernels_vs_oracle(cuda_device):
         assert abs(n - tn) < 1e-5 * max(n, 1e-3), (n, tn)
         for a, t in zip(ps, tp):
             assert np.abs(a - t.detach().cpu().numpy()).max() < 2e-6
+
+
+def test_sync_batchnorm_kernels_equal_full_batch(cuda_device):
+    """cross-rank BatchNorm (SURVEY.md 8e parity mode): two half-batch 'ranks' whose column sums are added (the
+    all-reduce, emulated in-process) must reproduce the full-batch forward, statistics and input gradient; d_gamma /
+    d_beta stay per-rank sums that add up to the full-batch ones."""
+    from onssen_b200 import _lib
+    H, M = 40, 512
+    Hp = _lib.hp_of(H)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    y = (torch.randn(M, 2 * Hp, generator=g) * 1.7 + 0.3).to(cuda_device)
+    d_out = torch.randn(M, 2 * Hp, generator=g).to(cuda_device)
+    gamma = (torch.rand(2 * H, generator=g) + 0.5).to(cuda_device)
+    beta = torch.randn(2 * H, generator=g).to(cuda_device)
+    stats = lambda: (torch.zeros(2 * H, device=cuda_device), torch.ones(2 * H, device=cuda_device))
+    rm, rv = stats()
+    full_h, mean, invstd = _lib.bn_forward_f16(y, M, H, gamma, beta, rm, rv, 1e-5, 0.1, True, save_stats=True)
+    full_dy, full_dg, full_db = _lib.bn_backward(d_out, y, M, H, gamma, mean, invstd)
+    halves = [slice(0, M // 2), slice(M // 2, M)]
+
+    def two_pass(call):
+        local = []
+        for sl in halves:                                   # pass 1: collect every rank's local sums
+            call(sl, (lambda t: local.append(t.clone()), 2))
+        total = local[0] + local[1]
+        return [call(sl, (lambda t: t.copy_(total), 2)) for sl in halves]   # pass 2: 'all-reduced' sums
+
+    outs = two_pass(lambda sl, sync: _lib.bn_forward_f16(y[sl].contiguous(), M // 2, H, gamma, beta, *stats(), 1e-5, 0.1,
+                                                       True, save_stats=True, sync=sync))
+    for sl, (o_h, m2, i2) in zip(halves, outs):
+        assert torch.allclose(m2, mean, atol=1e-6) and torch.allclose(i2, invstd, rtol=1e-6)
+        assert (o_h.float() - full_h[sl].float()).abs().max() < 4e-3          # one fp16 ulp at |x| < 8
+    grads = two_pass(lambda sl, sync: _lib.bn_backward(d_out[sl].contiguous(), y[sl].contiguous(), M // 2, H, gamma, mean,
+                                                       invstd, sync=sync))
+    for sl, (dy, _, _) in zip(halves, grads):
+        assert torch.allclose(dy, full_dy[sl], atol=2e-6, rtol=1e-5)
+    assert torch.allclose(grads[0][1] + grads[1][1], full_dg, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(grads[0][2] + grads[1][2], full_db, rtol=1e-5, atol=1e-5)
