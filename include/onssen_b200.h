@@ -352,6 +352,17 @@ int onssen_bn_backward_apply(const float* d_out, const float* y, int M, int M_to
                              const float* save_mean, const float* save_invstd, const void* sums_total_f64, float* d_y,
                              float* d_gamma, float* d_beta, void* scratch, void* stream);
 
+/* ---- deep-clustering inference: VAD + K-means on the embeddings -> masks
+ * (egs/wsj0-2mix/deep_clustering/evaluate.py:36-41).  emb [N][D] (N = frames*F of ONE utterance, D <= 64),
+ * feature [N] log-magnitudes (NULL = every bin active); active = feature >= max(feature) - db_threshold/20;
+ * K <= 3 clusters, `iters` Lloyd iterations after a deterministic farthest-point seeding (sklearn's k-means++ RNG is
+ * not reproduced; partitions are compared up to label permutation).  masks [K][N] (K = 2: mask[0] = label,
+ * mask[1] = 1 - label on active bins, 0 elsewhere) and/or labels [N] int32 (-1 inactive).  scratch:
+ * onssen_kmeans_scratch_bytes() bytes. */
+size_t onssen_kmeans_scratch_bytes(void);
+int onssen_kmeans_masks(const float* emb, const float* feature, long long N, int D, int K, float db_threshold,
+                        int iters, float* masks, int32_t* labels, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "onssen_blstm_rec_bwd_set_trace": (None, [c_vp]),
     "onssen_clip_grad_norm": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "onssen_adam_step": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_ll, c_vp]),
+    "onssen_kmeans_scratch_bytes": (c_sz, []),
+    "onssen_kmeans_masks": (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_f, c_int, c_vp, c_vp, c_vp, c_vp]),
     "onssen_bn_stats": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "onssen_bn_forward_f16_stats": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp,
                                             c_vp, c_vp, c_vp]),
@@ -745,3 +747,19 @@ def adam_step(tables, rows, lr, beta1, beta2, eps, weight_decay, step):
     dev = tables.fill(rows)
     _check(lib.onssen_adam_step(_p(dev), _p(tables.chunks), tables.nchunks, OPT_CHUNK, float(lr), float(beta1),
                                 float(beta2), float(eps), float(weight_decay), int(step), _stream()), "onssen_adam_step")
+
+
+def kmeans_masks(emb, feature, K=2, db_threshold=40.0, iters=30, want_labels=False):
+    """emb (frames, F, D) or (N, D) of one utterance, feature (frames, F) or None -> masks (K, frames, F)
+    [, labels int32 (frames, F)]"""
+    lib = load()
+    D = emb.shape[-1]
+    N = emb.numel() // D
+    shape = tuple(emb.shape[:-1])
+    masks = torch.empty((K,) + shape, device=emb.device, dtype=torch.float32)
+    labels = torch.empty(shape, device=emb.device, dtype=torch.int32) if want_labels else None
+    scratch = torch.empty(lib.onssen_kmeans_scratch_bytes(), device=emb.device, dtype=torch.uint8)
+    rc = lib.onssen_kmeans_masks(_p(_req(emb, torch.float32)), _p(None if feature is None else _req(feature, torch.float32)),
+                                 N, D, K, float(db_threshold), int(iters), _p(masks), _p(labels), _p(scratch), _stream())
+    _check(rc, "onssen_kmeans_masks")
+    return (masks, labels) if want_labels else masks

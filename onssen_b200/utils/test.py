@@ -1,11 +1,11 @@
 """tester + per-model estimators -- /root/reference/onssen/utils/test.py:7-41 and the `get_est_sig` hooks of
 egs/wsj0-2mix/{deep_clustering,chimera}/evaluate.py.  mask x mixture STFT -> waveform runs on the device
-(onssen_istft_masked); KMeans on the active-bin embeddings stays sklearn on the host like the reference
-(out of scope) and SI-SDR is a few lines of torch (sdr.py is out of scope too)."""
+(onssen_istft_masked) and so does the VAD + K-means on the active-bin embeddings (onssen_kmeans_masks: Lloyd with a
+deterministic seeding instead of sklearn's RNG-driven k-means++; same partition up to the label order, which the
+permutation-invariant SI-SDR ignores).  SI-SDR is a few lines of torch (sdr.py is out of scope)."""
 import itertools
 import os
 
-import numpy as np
 import torch
 
 from .. import _lib
@@ -62,21 +62,14 @@ class tester_dc(tester):
     """egs/wsj0-2mix/deep_clustering/evaluate.py:10-47"""
 
     def get_est_sig(self, input, label, output):
-        from sklearn.cluster import KMeans
         feature_mix, = input
         embedding, = output
         stft_r, stft_i, sig_ref = label
-        B, frames, F = feature_mix.shape
         num_spk, nsample = sig_ref.shape[1], sig_ref.shape[2]
-        f = feature_mix[0]
-        active = f >= (f.max() - 40 / 20)                                    # evaluate.py:36
-        emb = embedding[0][active].cpu().numpy()
-        lab = KMeans(n_clusters=num_spk, random_state=0, n_init=10).fit_predict(emb)
-        masks = torch.zeros(1, num_spk, frames, F, device=f.device)
-        labt = torch.from_numpy(lab.astype(np.float32)).to(f.device)
-        masks[0, 0][active] = labt                                           # evaluate.py:40-41
-        masks[0, 1][active] = 1 - labt
-        return self.masked_istft(stft_r, stft_i, masks, nsample), sig_ref
+        # evaluate.py:34-41 (batch 1): VAD at max - 40/20, cluster the active embeddings, mask[0] = label,
+        # mask[1] = 1 - label -- one C-ABI call, nothing leaves the device
+        masks = _lib.kmeans_masks(embedding[0].float().contiguous(), feature_mix[0].float().contiguous(), num_spk, 40.0)
+        return self.masked_istft(stft_r, stft_i, masks.unsqueeze(0), nsample), sig_ref
 
 
 class tester_chimera(tester):

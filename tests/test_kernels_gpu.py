@@ -273,3 +273,27 @@ def test_istft_masked_vs_oracle(lib, n_fft, hop, ns):
     for b in range(B):
         w = O.synth_utterance(b, ns)[0]
         assert np.abs(got[b, 0] - w).max() < 1e-5 * np.abs(w).max() + 1e-7
+
+
+def test_kmeans_masks_match_sklearn_partition(cuda_device):
+    """VAD + 2-means on unit-norm embeddings (deep_clustering/evaluate.py:36-41) against the reference's own tool
+    (sklearn KMeans, random_state=0) up to the label permutation."""
+    from sklearn.cluster import KMeans
+    from onssen_b200 import _lib
+    rng = np.random.RandomState(2)
+    frames, F, D = 60, 33, 20
+    dirs = rng.standard_normal((2, D)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    which = rng.uniform(size=(frames, F)) < 0.4
+    emb = dirs[which.astype(int)] + 0.25 * rng.standard_normal((frames, F, D))
+    emb = (emb / np.linalg.norm(emb, axis=-1, keepdims=True)).astype(np.float32)
+    feature = rng.uniform(-4, 0, size=(frames, F)).astype(np.float32)
+    active = feature >= feature.max() - 2.0
+    masks, labels = _lib.kmeans_masks(torch.from_numpy(emb).to(cuda_device), torch.from_numpy(feature).to(cuda_device), 2,
+                                      40.0, want_labels=True)
+    masks, labels = masks.cpu().numpy(), labels.cpu().numpy()
+    assert ((labels >= 0) == active).all()                      # VAD is exact (same fp32 compare)
+    want = KMeans(n_clusters=2, random_state=0, n_init=10).fit_predict(emb[active])
+    got = labels[active]
+    agree = max((got == want).mean(), (got == 1 - want).mean())
+    assert agree > 0.999, agree
+    assert (masks[0][active] == got).all() and (masks[1][active] == 1 - got).all() and (masks[:, ~active] == 0).all()
