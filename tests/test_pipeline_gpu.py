@@ -64,6 +64,9 @@ def test_trainer_validate_and_tester_eval(cuda_device, tmp_path):
     args.optimizer = ob.utils.build_optimizer(args.model.parameters(), args.optimizer_options)
     args.loss_fn = ob.loss.loss_chimera_msa
     tr = ob.utils.trainer(args)
+    w0 = args.model.fc_mi.weight.detach().clone()
+    l = tr.train(0)                                       # 2 steps: device-side loss accumulation, clip + Adam kernels
+    assert np.isfinite(l) and not torch.equal(w0, args.model.fc_mi.weight.detach())
     v = tr.validate(0)
     assert np.isfinite(v) and os.path.exists(tmp_path / "ckpt" / "final.mdl")
     saved = torch.load(tmp_path / "ckpt" / "final.mdl", weights_only=False)
