@@ -229,6 +229,8 @@ def run_gpu(args):
         if world > 1:
             broadcast_parameters(model)
             model.grad_sync = GradSync()
+            if args.sync_bn:
+                ob.utils.ddp.enable_sync_batchnorm(model)
         opt = ob.utils.build_optimizer(model.parameters(), {"name": "adam", "lr": 1e-3})
 
         def train_step(ws, st):
@@ -302,8 +304,10 @@ def run_gpu(args):
         if ms_train is not None:
             line["train"] = {"value": world * B * KT / (ms_train.item() / 1e3), "unit": "utterances/s",
                              "ms_per_step": ms_train.item() / KT, "steps": KT, "loss_last": train_loss,
+                             "sync_bn": bool(args.sync_bn and world > 1),
                              "includes": "featurizer + forward + loss_dc + hand-written backward (BPTT) + "
-                                         "bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm_(5) + Adam"}
+                                         "bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm_(5) + Adam "
+                                         "(multi-tensor kernels of this repo)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -316,6 +320,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step figure")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="training figure with whole-batch BatchNorm statistics across ranks (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
