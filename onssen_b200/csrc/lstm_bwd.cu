@@ -311,34 +311,44 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
                          (((size_t)((s - 1) & 1) * 2 + dir) * nbb + bb) * frag_group + lane;
       for (int ksb = ks_begin; ksb < ks_end; ksb += KPW) {
         const int kse = min(ksb + KPW, ks_end);
-        {
-          // probe: the last-written n-tile of one fragment per producer CTA (8 k-steps each) of this k-range
-          unsigned int probe = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (max(ksb, ((ksb >> 3) + q) * 8) < kse) probe |= 1u << q;
-          while (probe) {
-            uint2 pv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (probe & (1u << q))
-                pv[q] = ld_relaxed_v2(bfr + ((size_t)max(ksb, ((ksb >> 3) + q) * 8) * NT + (NT - 1)) * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if ((probe & (1u << q)) && (pv[q].x & 0x40004000u) == fw && (pv[q].y & 0x40004000u) == fw)
-                probe &= ~(1u << q);
-          }
-        }
         uint2 bf[KPW][NT];
         unsigned long long pending = 0;
 #pragma unroll
         for (int uu = 0; uu < KPW; ++uu)
           if (ksb + uu < kse) pending |= (unsigned long long)((1u << NT) - 1u) << (NT * uu);
+        {
+          // probe the last-written n-tile of one fragment per producer CTA (8 k-steps each) of this k-range, and
+          // request a producer's fragments the moment ITS probe carries the step's flag bits: the transfers of the
+          // early producers overlap the wait for the late ones
+          const int p0 = ksb >> 3;
+          unsigned int prod_wait = 0;
 #pragma unroll
-        for (int uu = 0; uu < KPW; ++uu)
+          for (int q = 0; q < 4; ++q)
+            if (max(ksb, (p0 + q) * 8) < kse) prod_wait |= 1u << q;
+          while (prod_wait) {
+            uint2 pv[4];
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt)
-            if (pending & (1ull << (NT * uu + nt))) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * NT + nt) * 32);
+            for (int q = 0; q < 4; ++q)
+              if (prod_wait & (1u << q))
+                pv[q] = ld_relaxed_v2(bfr + ((size_t)max(ksb, (p0 + q) * 8) * NT + (NT - 1)) * 32);
+            unsigned int fresh = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if ((prod_wait & (1u << q)) && (pv[q].x & 0x40004000u) == fw && (pv[q].y & 0x40004000u) == fw)
+                fresh |= 1u << q;
+            if (fresh) {
+#pragma unroll
+              for (int uu = 0; uu < KPW; ++uu) {
+                const unsigned int q = (unsigned int)(((ksb + uu) >> 3) - p0);
+                if (((fresh >> q) & 1u) && ksb + uu < kse) {
+#pragma unroll
+                  for (int nt = 0; nt < NT; ++nt) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * NT + nt) * 32);
+                }
+              }
+              prod_wait &= ~fresh;
+            }
+          }
+        }
         if (ksb == ks_begin) gate_factors();   // overlaps the burst's round trip
         while (true) {
 #pragma unroll

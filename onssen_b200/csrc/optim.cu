@@ -75,16 +75,34 @@ adam_kernel(const OptTensor* __restrict__ tensors, const OptChunk* __restrict__ 
   const OptTensor tn = tensors[ck.tensor];
   const long long end = min(tn.n, ck.start + chunk_elems);
   const float step_size = lr / bc1;
-  for (long long i = ck.start + threadIdx.x; i < end; i += 256) {
-    float pv = tn.p[i];
-    float g = tn.g[i];
+  auto upd = [&](float& pv, float g, float& m, float& v) {
     if (weight_decay != 0.f) g += weight_decay * pv;
-    const float m = beta1 * tn.m[i] + (1.0f - beta1) * g;
-    const float v = beta2 * tn.v[i] + (1.0f - beta2) * g * g;
-    tn.m[i] = m;
-    tn.v[i] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    tn.p[i] = pv - step_size * (m / denom);
+    m = beta1 * m + (1.0f - beta1) * g;
+    v = beta2 * v + (1.0f - beta2) * g * g;
+    pv -= step_size * (m / (sqrtf(v) / bc2_sqrt + eps));
+  };
+  // chunk starts are multiples of chunk_elems; with 16-byte aligned tensors the body runs on float4
+  const bool vec = (((uintptr_t)tn.p | (uintptr_t)tn.g | (uintptr_t)tn.m | (uintptr_t)tn.v) & 15) == 0 &&
+                   (ck.start & 3) == 0;
+  long long i0 = ck.start;
+  if (vec) {
+    const long long n4 = (end - ck.start) / 4;
+    float4* p4 = reinterpret_cast<float4*>(tn.p + ck.start);
+    const float4* g4 = reinterpret_cast<const float4*>(tn.g + ck.start);
+    float4* m4 = reinterpret_cast<float4*>(tn.m + ck.start);
+    float4* v4 = reinterpret_cast<float4*>(tn.v + ck.start);
+    for (long long i = threadIdx.x; i < n4; i += 256) {
+      float4 pv = p4[i], m = m4[i], v = v4[i];
+      const float4 g = g4[i];
+      upd(pv.x, g.x, m.x, v.x); upd(pv.y, g.y, m.y, v.y); upd(pv.z, g.z, m.z, v.z); upd(pv.w, g.w, m.w, v.w);
+      p4[i] = pv; m4[i] = m; v4[i] = v;
+    }
+    i0 = ck.start + n4 * 4;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += 256) {
+    float pv = tn.p[i], m = tn.m[i], v = tn.v[i];
+    upd(pv, tn.g[i], m, v);
+    tn.p[i] = pv; tn.m[i] = m; tn.v[i] = v;
   }
 }
 

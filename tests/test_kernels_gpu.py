@@ -297,3 +297,29 @@ def test_kmeans_masks_match_sklearn_partition(cuda_device):
     agree = max((got == want).mean(), (got == 1 - want).mean())
     assert agree > 0.999, agree
     assert (masks[0][active] == got).all() and (masks[1][active] == 1 - got).all() and (masks[:, ~active] == 0).all()
+
+
+def test_recurrence_batch_limits_and_single_utterance(lib):
+    """edge sizes of the persistent launch: B=1 works, the largest supported batch works, one more utterance is
+    refused with ONSSEN_ERR_UNSUPPORTED (never a silent fallback)."""
+    H, T, I = 600, 3, 129
+    Hp = lib.hp_of(H)
+    rng = np.random.RandomState(0)
+    k = 1 / np.sqrt(H)
+    mkw = lambda *s: torch.from_numpy(rng.uniform(-k, k, s).astype(np.float32)).cuda()
+    wf = (mkw(4 * H, I), mkw(4 * H, H), mkw(4 * H), mkw(4 * H))
+    wr = (mkw(4 * H, I), mkw(4 * H, H), mkw(4 * H), mkw(4 * H))
+    _, whh_p, _ = lib.lstm_pack_layer(wf, wr, H, I, False, 0)
+
+    def run(B):
+        gates = torch.randn(T * B, 8 * Hp, device="cuda")
+        y_f = torch.full((T * B, 2 * Hp), float("nan"), device="cuda")
+        lib.blstm_rec_fwd(gates, whh_p, B, T, H, None, y_f)
+        torch.cuda.synchronize()
+        return y_f
+
+    assert torch.isfinite(run(1)).all()
+    bmax = (lib.load().onssen_num_sms() // (2 * (Hp // 32))) * 32     # slices that fit x 32 columns (96 on 148 SMs)
+    assert bmax >= 64 and torch.isfinite(run(bmax)).all()
+    with pytest.raises(lib.OnssenB200Error, match="UNSUPPORTED|unsupported|-2"):
+        run(bmax + 16)
