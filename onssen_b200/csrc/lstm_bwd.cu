@@ -311,62 +311,63 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
                          (((size_t)((s - 1) & 1) * 2 + dir) * nbb + bb) * frag_group + lane;
       for (int ksb = ks_begin; ksb < ks_end; ksb += KPW) {
         const int kse = min(ksb + KPW, ks_end);
+        // Fragment bookkeeping is per PRODUCER CTA (8 k-steps each, <= 4 producers in a warp's k-range), as bit masks
+        // over the k-step index uu: one loop body holds the probes, the (re)load of the requested k-steps with
+        // immediate offsets and the validation -- a few hundred instructions instead of several thousand, which
+        // matters because the whole step body streams through the instruction cache once per step.
+        const int p0 = ksb >> 3;
+        unsigned int seg[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int lo = max(ksb, (p0 + q) * 8) - ksb, hi = min(kse, (p0 + q + 1) * 8) - ksb;
+          seg[q] = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+        }
+        const unsigned int valid = seg[0] | seg[1] | seg[2] | seg[3];
+        unsigned int waiting = (seg[0] ? 1u : 0u) | (seg[1] ? 2u : 0u) | (seg[2] ? 4u : 0u) | (seg[3] ? 8u : 0u);
+        const uint2* base = bfr + (size_t)ksb * NT * 32;
         uint2 bf[KPW][NT];
-        unsigned long long pending = 0;
-#pragma unroll
-        for (int uu = 0; uu < KPW; ++uu)
-          if (ksb + uu < kse) pending |= (unsigned long long)((1u << NT) - 1u) << (NT * uu);
-        {
-          // probe the last-written n-tile of one fragment per producer CTA (8 k-steps each) of this k-range, and
-          // request a producer's fragments the moment ITS probe carries the step's flag bits: the transfers of the
-          // early producers overlap the wait for the late ones
-          const int p0 = ksb >> 3;
-          unsigned int prod_wait = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (max(ksb, (p0 + q) * 8) < kse) prod_wait |= 1u << q;
-          while (prod_wait) {
+        bool factors_done = ksb != ks_begin;
+        while (true) {
+          unsigned int issue = 0;
+          if (waiting) {
+            // probe the last-written n-tile of the first k-step of every producer still waited for; a producer's
+            // k-steps are requested the moment ITS probe carries the step's flag bits (early transfers overlap the
+            // wait for late producers)
             uint2 pv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              if (prod_wait & (1u << q))
+              if (waiting & (1u << q))
                 pv[q] = ld_relaxed_v2(bfr + ((size_t)max(ksb, (p0 + q) * 8) * NT + (NT - 1)) * 32);
-            unsigned int fresh = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              if ((prod_wait & (1u << q)) && (pv[q].x & 0x40004000u) == fw && (pv[q].y & 0x40004000u) == fw)
-                fresh |= 1u << q;
-            if (fresh) {
-#pragma unroll
-              for (int uu = 0; uu < KPW; ++uu) {
-                const unsigned int q = (unsigned int)(((ksb + uu) >> 3) - p0);
-                if (((fresh >> q) & 1u) && ksb + uu < kse) {
-#pragma unroll
-                  for (int nt = 0; nt < NT; ++nt) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * NT + nt) * 32);
-                }
+              if ((waiting & (1u << q)) && (pv[q].x & 0x40004000u) == fw && (pv[q].y & 0x40004000u) == fw) {
+                issue |= seg[q];
+                waiting &= ~(1u << q);
               }
-              prod_wait &= ~fresh;
+          } else {
+            if (!factors_done) {   // overlaps the round trip of the last requests
+              gate_factors();
+              factors_done = true;
             }
+            // every k-step has been requested at least once: validate, re-request the stale ones
+            unsigned int stale = 0;
+#pragma unroll
+            for (int uu = 0; uu < KPW; ++uu) {
+              unsigned int t = 0;
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) t |= (bf[uu][nt].x ^ fw) | (bf[uu][nt].y ^ fw);
+              if (t & 0x40004000u) stale |= 1u << uu;
+            }
+            stale &= valid;
+            if (!stale) break;
+            issue = stale;
           }
-        }
-        if (ksb == ks_begin) gate_factors();   // overlaps the burst's round trip
-        while (true) {
 #pragma unroll
           for (int uu = 0; uu < KPW; ++uu)
+            if (issue & (1u << uu)) {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-              if ((pending & (1ull << (NT * uu + nt))) && (bf[uu][nt].x & 0x40004000u) == fw &&
-                  (bf[uu][nt].y & 0x40004000u) == fw) {
-                bf[uu][nt].x &= ~0x40004000u;
-                bf[uu][nt].y &= ~0x40004000u;
-                pending &= ~(1ull << (NT * uu + nt));
-              }
-          if (!pending) break;
-#pragma unroll
-          for (int uu = 0; uu < KPW; ++uu)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-              if (pending & (1ull << (NT * uu + nt))) bf[uu][nt] = ld_relaxed_v2(bfr + ((size_t)(ksb + uu) * NT + nt) * 32);
+              for (int nt = 0; nt < NT; ++nt) bf[uu][nt] = ld_relaxed_v2(base + (uu * NT + nt) * 32);
+            }
         }
         BWD_TRACE(1);
         // A fragments double-buffered in registers: the shared-memory load of k-step uu+1 is in flight during the
@@ -382,8 +383,9 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
             an1 = a_s[((size_t)kn * 2 + 1) * 32 + lane];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-              mma_16816(acc[0][nt], reinterpret_cast<const uint32_t*>(&a0), reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
-              mma_16816(acc[1][nt], reinterpret_cast<const uint32_t*>(&a1), reinterpret_cast<const uint32_t*>(&bf[uu][nt]));
+              const uint2 bv = make_uint2(bf[uu][nt].x & ~0x40004000u, bf[uu][nt].y & ~0x40004000u);   // strip the flags
+              mma_16816(acc[0][nt], reinterpret_cast<const uint32_t*>(&a0), reinterpret_cast<const uint32_t*>(&bv));
+              mma_16816(acc[1][nt], reinterpret_cast<const uint32_t*>(&a1), reinterpret_cast<const uint32_t*>(&bv));
             }
           }
         }
