@@ -205,6 +205,29 @@ __device__ __forceinline__ __half to_half_flag_range(float x) {   // clamp to th
 // (tanh, dropout, the products of saved activations) is computed while the burst is in flight, which leaves
 // ~10 dependent instructions between the partial-sum barrier and the publish stores; (3) the publish stores go
 // before the dG stores that only the later GEMMs read.
+// shared-memory accesses by 32-bit shared address (no generic->shared conversion on the critical path)
+__device__ __forceinline__ uint32_t smem_addr32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 lds_v2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+// pin a value in a register: without this ptxas re-derives loop invariants from special registers (S2R / S2UR of
+// %ctaid, the shared window base) and constant-bank loads INSIDE the step loop, on the critical path after the barrier
+template <typename Tp>
+__device__ __forceinline__ void pin(Tp*& x) { asm volatile("" : "+l"(x)); }
+__device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
+
 template <int NT>
 __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdParams p) {
   constexpr int KPW = NT == 2 ? 19 : 8;      // fragment k-steps held in registers at once (NT*KPW uint2 per lane)
@@ -258,6 +281,23 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
     pub_off[i] = (unsigned int)((((size_t)ks * NT + (bl >> 3)) * 32 + (bl & 7) * 4 + (j & 1) * 2) * 2 + (j >> 1));
     row_off[i] = (long long)min(b0 + bl, B - 1) * (2 * G4) + dir * G4 + ub * 128 + 4 * ul;
   }
+  // loop invariants of the latency-critical parts, pinned in registers (by step parity)
+  const uint2* bfr_par[2];    // this CTA's (dir, bb) fragment group, + lane: what it consumes
+  uint32_t* fb_par[2];        // ... and what it publishes into
+  uint32_t red_wr32[2], red_rd32[2];
+  uint32_t valid_items = 0;
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    bfr_par[par] = reinterpret_cast<const uint2*>(p.frag) + (((size_t)par * 2 + dir) * nbb + bb) * frag_group + lane;
+    fb_par[par] = p.frag + (((size_t)par * 2 + dir) * nbb + bb) * frag_group * 2;
+    red_wr32[par] = smem_addr32(red + par * RED_STEP + (warp * 2 * NT) * 32 + lane);
+    red_rd32[par] = smem_addr32(reinterpret_cast<const float*>(red + par * RED_STEP + my_tile * 32 + lane) + my_v0);
+    pin(bfr_par[par]); pin(fb_par[par]); pin(red_wr32[par]); pin(red_rd32[par]);
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i)
+    if (b0 + item_bl[i] < B) valid_items |= 1u << i;
+  pin(valid_items);
 
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? T - 1 - s : s;
@@ -307,8 +347,7 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
           for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
       const unsigned int fbit = ((((unsigned int)(s - 1)) >> 1) & 1u) ^ 1u;
       const unsigned int fw = fbit ? 0x40004000u : 0u;
-      const uint2* bfr = reinterpret_cast<const uint2*>(p.frag) +
-                         (((size_t)((s - 1) & 1) * 2 + dir) * nbb + bb) * frag_group + lane;
+      const uint2* bfr = ((s - 1) & 1) ? bfr_par[1] : bfr_par[0];
       for (int ksb = ks_begin; ksb < ks_end; ksb += KPW) {
         const int kse = min(ksb + KPW, ks_end);
         // Fragment bookkeeping is per PRODUCER CTA (8 k-steps each, <= 4 producers in a warp's k-range), as bit masks
@@ -346,6 +385,11 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
               }
           } else {
             if (!factors_done) {   // overlaps the round trip of the last requests
+              // keep the compiler from hoisting this block above the probes: it consumes the step's prefetched
+              // activations (HBM latency) and would stall the warp before its first poll
+#pragma unroll
+              for (int i = 0; i < ITEMS; ++i)
+                asm volatile("" : "+f"(a4[i].x), "+f"(a4[i].y), "+f"(a4[i].z), "+f"(a4[i].w), "+f"(ct[i]), "+f"(cprev[i]));
               gate_factors();
               factors_done = true;
             }
@@ -395,8 +439,8 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-          red[(s & 1) * RED_STEP + (warp * 2 * NT + mt * NT + nt) * 32 + lane] =
-              make_float4(acc[mt][nt][0], acc[mt][nt][1], acc[mt][nt][2], acc[mt][nt][3]);
+          sts_v4(((s & 1) ? red_wr32[1] : red_wr32[0]) + (mt * NT + nt) * 32 * 16,
+                 make_float4(acc[mt][nt][0], acc[mt][nt][1], acc[mt][nt][2], acc[mt][nt][3]));
     } else {
       gate_factors();
     }
@@ -406,20 +450,20 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
     // ---- phase B: gate derivatives of this CTA's units at step t; publish dG in B-fragment order
     const unsigned int fbit_w = ((((unsigned int)s) >> 1) & 1u) ^ 1u;
     const unsigned int fww = fbit_w ? 0x40004000u : 0u;
-    uint32_t* fb = p.frag + (((size_t)(s & 1) * 2 + dir) * nbb + bb) * frag_group * 2;
+    uint32_t* fb = (s & 1) ? fb_par[1] : fb_par[0];
     float4 d4v[ITEMS];
     uint2 ov[ITEMS];
     float rsum[ITEMS];
     if (s > 0) {
-      const float* rp = reinterpret_cast<const float*>(red + (s & 1) * RED_STEP + my_tile * 32 + lane) + my_v0;
+      const uint32_t rp = (s & 1) ? red_rd32[1] : red_rd32[0];
       float r[8][ITEMS];
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
         if (NT == 2) {
-          const float2 v = *reinterpret_cast<const float2*>(rp + (size_t)w * 2 * NT * 32 * 4);
+          const float2 v = lds_v2(rp + w * (2 * NT * 32 * 16));
           r[w][0] = v.x; r[w][1] = v.y;
         } else {
-          const float4 v = *reinterpret_cast<const float4*>(rp + (size_t)w * 2 * NT * 32 * 4);
+          const float4 v = lds_v4(rp + w * (2 * NT * 32 * 16));
           r[w][0] = v.x; r[w][1] = v.y; r[w][ITEMS - 2] = v.z; r[w][ITEMS - 1] = v.w;
         }
       }
@@ -437,7 +481,7 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
       // scaled values (the k_* carry the loss scale); the fp32 copy is unscaled again below
       const float s_i = dct * k_i[i], s_f = dct * k_f[i], s_g = dct * k_g[i], s_o = dh * k_o[i];
       uint2 o = make_uint2(0u, 0u);
-      if ((b0 + bl) < B) {   // pad batch columns publish zeros so that every fragment entry turns fresh
+      if (valid_items & (1u << i)) {   // pad batch columns publish zeros so that every fragment entry turns fresh
         __half2 lo = __halves2half2(to_half_flag_range(s_i), to_half_flag_range(s_f));
         __half2 hi = __halves2half2(to_half_flag_range(s_g), to_half_flag_range(s_o));
         o.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -453,7 +497,7 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
     BWD_TRACE(6);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      if ((b0 + item_bl[i]) < B) {
+      if (valid_items & (1u << i)) {
         const long long off = (long long)t * B * (2 * G4) + row_off[i];
         *reinterpret_cast<float4*>(p.actg + off) = d4v[i];
         *reinterpret_cast<uint2*>(p.dg16 + off) = ov[i];

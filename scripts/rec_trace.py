@@ -3,6 +3,8 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from onssen_b200 import _lib
+if os.environ.get("ONSSEN_LIB"):
+    _lib.LIB_PATH = os.environ["ONSSEN_LIB"]      # A/B runs against another build of the library
 
 B, T, H = int(os.environ.get("B", 32)), 400, 600
 lib = _lib.load()
