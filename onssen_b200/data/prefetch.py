@@ -4,8 +4,9 @@ while the model runs batch i on the main stream.
 The reference featurizes inline on the host inside `for data in train_loader` (onssen/utils/train.py:75, SURVEY.md
 section 3.2 "the real wall-clock bottleneck"); here the whole featurizer is two kernel launches, and the
 persistent recurrence leaves ~34 of 148 SMs idle.  Measured on B200 (cfg2): useful when the
-consumer synchronises every step (it hides the H2D copy), but NOT in a free-running loop -- thousands of STFT blocks
-delay the co-residency of the cooperative recurrent kernel (7.7k -> 5.4k utt/s) -- so bench.py featurizes inline."""
+consumer synchronises every step (it hides the H2D copy), but NOT in a free-running loop: STFT blocks co-reside on the
+SMs of the latency-bound persistent recurrent CTAs and take issue slots from them (8.0k -> 6.9k utt/s; 6.0k with the
+model on a high-priority stream, which only changes which blocks are placed first) -- so bench.py featurizes inline."""
 import torch
 
 from . import feature_utils
