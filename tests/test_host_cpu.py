@@ -88,3 +88,28 @@ def test_bench_reference_arm_line_contract(monkeypatch, capsys):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["metric"] == bench.METRIC
+
+
+def test_egs_configs_match_constructor_and_loader_signatures():
+    """every egs/*/config.json parses into the AttrDict shim, its model_options are accepted by the model its run.py
+    builds, and its feature_options carry what the loader reads"""
+    import glob
+    import inspect
+    import json
+    import onssen_b200 as ob
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "egs")
+    model_of = {"deep_clustering": ob.nn.deep_clustering, "chimera": ob.nn.chimera, "edinburgh_tts": ob.nn.chimera,
+                "daps": ob.nn.enhance, "phase-net": ob.nn.phase_net}
+    seen = 0
+    for cfg in glob.glob(os.path.join(root, "**", "config.json"), recursive=True):
+        args = ob.utils.AttrDict(json.load(open(cfg)))
+        key = next(k for k in model_of if k in cfg.replace(os.sep, "/").split("/egs/")[1])
+        params = inspect.signature(model_of[key].__init__).parameters
+        assert set(args["model_options"]) <= set(params), (cfg, set(args["model_options"]) - set(params))
+        fo = args.feature_options
+        for k in ("data_path", "batch_size", "frame_length", "sampling_rate", "window_size", "hop_size"):
+            assert k in fo, (cfg, k)
+        assert args.model_options.input_dim == fo.window_size // 2 + 1
+        assert str(args.device).startswith("cuda") and os.path.exists(os.path.join(os.path.dirname(cfg), "run.py"))
+        seen += 1
+    assert seen == 6
