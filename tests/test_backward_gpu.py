@@ -215,3 +215,37 @@ def test_sync_batchnorm_kernels_equal_full_batch(cuda_device):
         assert torch.allclose(dy, full_dy[sl], atol=2e-6, rtol=1e-5)
     assert torch.allclose(grads[0][1] + grads[1][1], full_dg, rtol=1e-5, atol=1e-5)
     assert torch.allclose(grads[0][2] + grads[1][2], full_db, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B", [20, 32, 64])
+def test_bptt_persistent_kernel_matches_per_step_kernel(cuda_device, B):
+    """differential test of the two BPTT implementations on the same random state: the persistent cooperative kernel
+    (NT=2 batch blocks at B<=48, NT=4 at B=64, pad columns at B=20) against the one-launch-per-step kernel"""
+    from onssen_b200 import _lib
+    lib = _lib.load()
+    H, T = 600, 5
+    Hp, M = _lib.hp_of(H), T * B
+    g = torch.Generator(device="cpu").manual_seed(B)
+    k = 1 / np.sqrt(H)
+    mk = lambda *s: ((torch.rand(*s, generator=g) * 2 - 1) * k).to(cuda_device)
+    whh_t = _lib.lstm_pack_whh_t(mk(4 * H, H), mk(4 * H, H), H)
+    act0 = torch.rand(M, 8 * Hp, generator=g).to(cuda_device)
+    c = torch.randn(M, 2 * Hp, generator=g).to(cuda_device)
+    dy = (torch.randn(M, 2 * Hp, generator=g) * 1e-3).to(cuda_device)
+    sc = _lib.amax_scale(dy, target=0.0625)
+    outs = []
+    try:
+        for mode in (0, 1):
+            lib.onssen_blstm_rec_bwd_set_persistent(mode)
+            act = act0.clone()
+            dg16 = torch.zeros(M, 8 * Hp, device=cuda_device, dtype=torch.float16)
+            _lib.blstm_rec_bwd(act, dg16, c, dy, whh_t, sc, B, T, H, 0.3, 7, 1)
+            torch.cuda.synchronize()
+            outs.append((act, dg16))
+    finally:
+        lib.onssen_blstm_rec_bwd_set_persistent(1)
+    (a0, h0), (a1, h1) = outs
+    scale = a0.abs().max().item()
+    assert scale > 0 and torch.isfinite(a1).all()
+    assert (a0 - a1).abs().max().item() < 2e-4 * scale            # same operands, different summation order
+    assert (h0.float() - h1.float()).abs().max().item() <= 2e-3 * h0.float().abs().max().item()
