@@ -147,7 +147,8 @@ def dc_forward_train(model, x):
     M = T * B
     layers, packed, y_f = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=True)
     a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True, sync=bn_sync(model))
+                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True,
+                                            sync=bn_sync(model))
     bn.num_batches_tracked += 1
     w_p = model._fc_cache.get([model.fc_dc.weight], lambda: _lib.pack_linear_f16(model.fc_dc.weight, True, H))
     emb = torch.empty(B, T, F, D, device=x.device, dtype=torch.float32)
@@ -239,7 +240,8 @@ def enhance_forward_train(model, x_and_noisy):
     dev = x.device
     layers, packed, y_f = blstm_forward_train(rnn, model._rnn_cache, x, model.training, last_f32=True)
     a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True, sync=bn_sync(model))
+                                            bn.running_var, bn.eps, bn.momentum, True, save_stats=True,
+                                            sync=bn_sync(model))
     bn.num_batches_tracked += 1
     w_mi = model._mi.get([model.fc_mi.weight], lambda: _lib.pack_linear_f16(model.fc_mi.weight, True, H))
     w_pre = model._pre.get([model.fc_pre.weight], lambda: _lib.pack_linear_f16(model.fc_pre.weight, False))
@@ -293,7 +295,8 @@ def phase_forward_train(model, inp):
         xin = _lib.pack_phase_input_f16(x_mag, mk, mk.stride(-1), x_phase)
         layers, packed, y_f = blstm_forward_train_packed(model.rnn, model._rnn_cache, xin, B, T, model.training, True)
         a_h, mean, invstd = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                                bn.running_var, bn.eps, bn.momentum, True, save_stats=True, sync=bn_sync(model))
+                                                bn.running_var, bn.eps, bn.momentum, True, save_stats=True,
+                                            sync=bn_sync(model))
         bn.num_batches_tracked += 1
         ph = torch.empty(B, T, F, 2, device=x_mag.device, dtype=torch.float32)
         _lib.gemm_f16(a_h, w_ph, model.fc_phase.bias.detach(), ph, M, 2 * F, a_h.shape[1], 2 * F, remap_inner=B,

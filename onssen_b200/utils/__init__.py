@@ -5,5 +5,5 @@ from .train import trainer
 from .optim import Adam, clip_grad_norm_
 from . import ddp, dist, optim
 
-__all__ = ["AttrDict", "AverageMeter", "build_optimizer", "trainer", "tester", "tester_dc", "tester_chimera", "dist", "ddp", "optim", "Adam",
-           "clip_grad_norm_"]
+__all__ = ["AttrDict", "AverageMeter", "build_optimizer", "trainer", "tester", "tester_dc", "tester_chimera",
+           "dist", "ddp", "optim", "Adam", "clip_grad_norm_"]
