@@ -285,7 +285,7 @@ def run_gpu(args):
                     "share_of_step": float(np.sum(rec_ms)) / ms.item(),
                     "tensor_alt": {"flops_per_launch": flops, "achieved_tflops": flops / (rec_avg_ms * 1e-3) / 1e12,
                                    "peak_tflops": pk.get("bf16_tflops_sustained")},
-                    "note": "weights are SMEM-resident, so real DRAM traffic is only the gate/y streams; the "
+                    "note": "weights are TMEM-resident, so real DRAM traffic is only the gate/y streams; the "
                             "weight-stream model is the SURVEY 8(d) bound a non-persistent kernel would hit"}
         cores = os.cpu_count()
         sample = 8
