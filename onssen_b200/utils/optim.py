@@ -16,6 +16,8 @@ def _rows(params, with_state=None):
         g = p.grad
         if not g.is_contiguous():
             p.grad = g = g.contiguous()
+        if not (p.is_cuda and g.is_cuda):
+            raise _lib.OnssenB200Error("optimiser kernels run on CUDA tensors only (no CPU fallback by design)")
         if g.dtype != torch.float32 or p.dtype != torch.float32 or not p.is_contiguous():
             raise _lib.OnssenB200Error("optimiser kernels need contiguous fp32 parameters and gradients")
         st = (0, 0) if with_state is None else (with_state[p]["exp_avg"].data_ptr(), with_state[p]["exp_avg_sq"].data_ptr())

@@ -59,12 +59,36 @@ def _worker(rank, world, port, ret):
         lin.weight.fill_(float(rank))
     broadcast_parameters(lin, 0)
     assert float(lin.weight.abs().max()) == 0.0
+    # rank-aware trainer: parameters broadcast from rank 0, validation loss averaged over ranks (identical early-stop
+    # decisions), only rank 0 writes the checkpoint.  A torch-only stand-in model: the trainer is model-agnostic.
+    from onssen_b200.utils import AttrDict, trainer
+    model = torch.nn.Linear(3, 1)
+    with torch.no_grad():
+        model.weight.fill_(1.0 + rank)
+        model.bias.fill_(0.0)
+    batches = [([torch.full((2, 3), float(rank + 1 + i))], [torch.zeros(2, 1)]) for i in range(3)]
+    ckpt = os.path.join(os.environ["ONSSEN_TEST_TMP"], "ckpt")
+    args = AttrDict({"model_name": "dc", "device": "cpu", "num_epoch": 1, "checkpoint_path": ckpt, "verbose": False,
+                     "model": model, "train_loader": batches, "valid_loader": batches,
+                     "loss_fn": lambda out, lab: (out[0] - lab[0]).abs(),
+                     "optimizer": torch.optim.SGD(model.parameters(), lr=0.1)})
+    model_call = model.forward
+    model.forward = lambda inp: [model_call(inp[0])]             # plugin contract: list in, list out
+    tr = trainer(args)
+    assert torch.equal(model.weight, torch.ones(1, 3)) and model.grad_sync is not None     # rank 0's parameters
+    cv = tr.validate(0)
+    mine = sum(3.0 * (rank + 1 + i) for i in range(3)) / 3
+    both = sum(sum(3.0 * (r + 1 + i) for i in range(3)) / 3 for r in range(world)) / world
+    assert abs(cv - both) < 1e-5 and abs(mine - both) > 0.1, (cv, mine, both)
+    dist.barrier()
+    assert os.path.exists(os.path.join(ckpt, "final.mdl")) and tr.rank == rank and tr.world == world
     ret[rank] = (got, naive, want)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharding_and_reductions_world2():
+def test_sharding_and_reductions_world2(tmp_path):
+    os.environ["ONSSEN_TEST_TMP"] = str(tmp_path)
     world = 2
     port = _free_port()
     ctx = mp.get_context("spawn")
