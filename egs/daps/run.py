@@ -1,37 +1,21 @@
-"""python run.py -c config.json -- enhancement BLSTM with restoration layers on DAPS noisy/clean pairs.
-
-Working counterpart of the reference's egs/daps/run.py:1-31 (same defects as egs/edinburgh_tts/run.py; also
-`enhance` does not take the `output_dim` its config passes, enhancement.py:12-18 vs egs/daps/config.json:18 -- the key
-is dropped here).  An epoch is `train_num_batch` batches of consecutive frame_length-frame segments."""
-import argparse
-import json
+"""Enhancement BLSTM with restoration layers on DAPS noisy/clean pairs.  Working counterpart of the reference's
+egs/daps/run.py:1-31 (same defects as its Edinburgh script; `enhance` also does not take the `output_dim` that
+egs/daps/config.json:18 passes -- dropped here).  An epoch is `<partition>_num_batch` batches of consecutive segments."""
 import os
 import sys
 
-sys.path.append(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.append(os.path.join(HERE, "..", ".."))
 
-import torch
-
-from onssen_b200 import data, loss, nn, utils
-from onssen_b200.utils import AttrDict
+from onssen_b200 import data, loss, nn
+from onssen_b200.utils.experiment import load_config, run_experiment
 
 
-def main():
-    parser = argparse.ArgumentParser(description='Parse the config path')
-    parser.add_argument("-c", "--config", dest="path", help='The path to the config file. e.g. python run.py --config config.json')
-    config = parser.parse_args()
-    with open(config.path) as f:
-        args = AttrDict(json.load(f))
-    device = torch.device(args.device)
-    options = {k: v for k, v in args['model_options'].items() if k != "output_dim"}
-    args.model = nn.enhance(**options)
-    args.model.to(device)
-    args.train_loader = data.daps_enhance_dataloader(args.train_num_batch, args.feature_options, 'train', device)
-    args.valid_loader = data.daps_enhance_dataloader(args.validate_num_batch, args.feature_options, 'validation', device)
-    args.optimizer = utils.build_optimizer(args.model.parameters(), args.optimizer_options)
-    args.loss_fn = loss.loss_mask_msa
-    utils.trainer(args).run()
+def loader(args, partition, device):
+    n = args.train_num_batch if partition == "train" else args.validate_num_batch
+    return data.daps_enhance_dataloader(n, args.feature_options, partition, device)
 
 
 if __name__ == "__main__":
-    main()
+    run_experiment(load_config(HERE), nn.enhance, loader, loss.loss_mask_msa, ("train", "validation"),
+                   drop_model_keys=("output_dim",))

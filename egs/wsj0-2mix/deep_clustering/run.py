@@ -1,35 +1,18 @@
-"""python run.py -c config.json -- the reference entry point (egs/wsj0-2mix/deep_clustering/run.py:13-34) with
-the import line swapped to onssen_b200 (and the uninstallable `attrdict` replaced by the in-repo shim)."""
-import argparse
-import json
+"""Deep clustering on wsj0-2mix: `python run.py -c config.json` (what egs/wsj0-2mix/deep_clustering/run.py:13-34 and
+evaluate.py of the reference do, on onssen_b200: training, then SI-SDR of the K-means masks on `tt`)."""
 import os
 import sys
 
-sys.path.append(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", ".."))
-
-import torch
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.append(os.path.join(HERE, "..", "..", ".."))
 
 from onssen_b200 import data, loss, nn, utils
-from onssen_b200.utils import AttrDict
+from onssen_b200.utils.experiment import load_config, run_experiment
 
 
-def main():
-    parser = argparse.ArgumentParser(description='Parse the config path')
-    parser.add_argument("-c", "--config", dest="path", help='The path to the config file. e.g. python run.py --config config.json')
-    config = parser.parse_args()
-    with open(config.path) as f:
-        args = AttrDict(json.load(f))
-    device = torch.device(args.device)
-    args.model = nn.deep_clustering(**(args['model_options']))
-    args.model.to(device)
-    args.train_loader = data.wsj0_2mix_dataloader(args.model_name, args.feature_options, 'tr', device)
-    args.valid_loader = data.wsj0_2mix_dataloader(args.model_name, args.feature_options, 'cv', device)
-    args.test_loader = data.wsj0_2mix_dataloader(args.model_name, args.feature_options, 'tt', device)
-    args.optimizer = utils.build_optimizer(args.model.parameters(), args.optimizer_options)
-    args.loss_fn = loss.loss_dc
-    utils.trainer(args).run()
-    print("SI-SDR: %.2f" % utils.tester_dc(args).eval())
+def loader(args, partition, device):
+    return data.wsj0_2mix_dataloader(args.model_name, args.feature_options, partition, device)
 
 
 if __name__ == "__main__":
-    main()
+    run_experiment(load_config(HERE), nn.deep_clustering, loader, loss.loss_dc, ("tr", "cv", "tt"), utils.tester_dc)

@@ -3,7 +3,7 @@ from .basic import AttrDict, AverageMeter, build_optimizer
 from .test import tester, tester_chimera, tester_dc
 from .train import trainer
 from .optim import Adam, clip_grad_norm_
-from . import ddp, dist, optim
+from . import ddp, dist, experiment, optim
 
 __all__ = ["AttrDict", "AverageMeter", "build_optimizer", "trainer", "tester", "tester_dc", "tester_chimera",
-           "dist", "ddp", "optim", "Adam", "clip_grad_norm_"]
+           "dist", "ddp", "optim", "experiment", "Adam", "clip_grad_norm_"]

@@ -113,3 +113,16 @@ def test_egs_configs_match_constructor_and_loader_signatures():
         assert str(args.device).startswith("cuda") and os.path.exists(os.path.join(os.path.dirname(cfg), "run.py"))
         seen += 1
     assert seen == 6
+
+
+def test_experiment_config_loading(tmp_path):
+    import json
+    from onssen_b200.utils.experiment import load_config
+    (tmp_path / "config.json").write_text(json.dumps({"device": "cuda:0", "model_options": {"input_dim": 129}}))
+    (tmp_path / "other.json").write_text(json.dumps({"device": "cuda:1", "model_options": {"input_dim": 257}}))
+    a = load_config(str(tmp_path), argv=[])
+    assert a.device == "cuda:0" and a.model_options.input_dim == 129 and a["model_options"]["input_dim"] == 129
+    b = load_config(str(tmp_path), argv=["-c", str(tmp_path / "other.json")])
+    assert b.device == "cuda:1"
+    b.model = object()                       # runtime objects are assigned onto the same mapping (run.py:23-29 usage)
+    assert "model" in b
