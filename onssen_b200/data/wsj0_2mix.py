@@ -22,16 +22,27 @@ from . import feature_utils
 
 
 def _read_wav(fn, sampling_rate):
+    """PCM -> mono float32 at `sampling_rate` (feature_utils.py:15-19: librosa.load(sr=None) then
+    librosa.core.resample when the file's rate differs).  Resampling stays on the host like in the reference, as a
+    polyphase filter (scipy.signal.resample_poly); librosa's default kernel (resampy kaiser_best, version unpinned)
+    is a different low-pass, so resampled audio is NOT sample-identical to the reference's: parity unpinned for files
+    whose rate differs from the configured one (wsj0-2mix 8 kHz needs no resampling)."""
     from scipy.io import wavfile
     rate, x = wavfile.read(fn)
-    assert rate == sampling_rate, f"{fn}: sampling rate {rate} != {sampling_rate} (resampling is not part of this path)"
     if x.dtype == np.int16:
         x = x.astype(np.float32) / 32768.0
     elif x.dtype == np.int32:
         x = x.astype(np.float32) / 2147483648.0
     else:
         x = x.astype(np.float32)
-    return x if x.ndim == 1 else x.mean(axis=1)
+    if x.ndim > 1:
+        x = x.mean(axis=1)
+    if rate != sampling_rate:
+        from math import gcd
+        from scipy.signal import resample_poly
+        g = gcd(int(rate), int(sampling_rate))
+        x = resample_poly(x, int(sampling_rate) // g, int(rate) // g).astype(np.float32)
+    return x
 
 
 def _opt(feature_options, key):

@@ -180,3 +180,18 @@ def test_daps_segment_cursor_semantics(tmp_path):
     ld = daps_enhance_dataloader(3, dict(data_path=str(tmp_path), batch_size=2, frame_length=10, sampling_rate=16000,
                                          window_size=512, hop_size=128), "train")
     assert len(ld) == 3 and ld.clean_path("/x/f1_script2_iphone.wav") == str(tmp_path) + "/clean/f1_script2_clean.wav"
+
+
+def test_read_wav_resamples_on_the_host(tmp_path):
+    """files at another rate are brought to feature_options.sampling_rate (feature_utils.py:15-19 behaviour)"""
+    from scipy.io import wavfile
+    from onssen_b200.data.wsj0_2mix import _read_wav
+    t = np.arange(48000) / 48000.0
+    x = (0.5 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    wavfile.write(str(tmp_path / "a.wav"), 48000, (x * 32767).astype(np.int16))
+    y = _read_wav(str(tmp_path / "a.wav"), 16000)
+    assert y.dtype == np.float32 and y.shape == (16000,)
+    ref = 0.5 * np.sin(2 * np.pi * 440 * np.arange(16000) / 16000.0)
+    assert np.abs(y[200:-200] - ref[200:-200]).max() < 2e-3          # a 440 Hz tone survives 48 -> 16 kHz unchanged
+    same = _read_wav(str(tmp_path / "a.wav"), 48000)
+    assert same.shape == (48000,) and np.abs(same - (x * 32767).astype(np.int16) / 32768.0).max() < 1e-7
