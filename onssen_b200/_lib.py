@@ -719,18 +719,17 @@ class OptTables:
         self.nchunks = len(ch)
         self.chunks = torch.from_numpy(np.array(ch, dtype=np.int64).reshape(-1, 2)).to(device)
         self.partials = torch.empty(self.nchunks, device=device, dtype=torch.float64)
-        # pageable on purpose: the runtime stages a pageable source before cudaMemcpyAsync returns, so the buffer can be
-        # refilled for the next call while earlier copies are still queued (the loop never synchronises)
-        self.host = torch.empty(len(self.numels), 5, dtype=torch.int64)
         self.dev = torch.empty(len(self.numels), 5, device=device, dtype=torch.int64)
 
     def fill(self, rows):
-        """rows: iterable of (param_ptr, grad_ptr, m_ptr, v_ptr) ints; numel comes from the constructor."""
-        for i, r in enumerate(rows):
-            for j in range(4):
-                self.host[i, j] = r[j]
-            self.host[i, 4] = self.numels[i]
-        self.dev.copy_(self.host, non_blocking=True)
+        """rows: sequence of (param_ptr, grad_ptr, m_ptr, v_ptr) ints; numel comes from the constructor.  The source of
+        the copy is a fresh PAGEABLE array: the runtime stages pageable memory before cudaMemcpyAsync returns, so
+        nothing has to outlive this call although the loop never synchronises."""
+        import numpy as np
+        arr = np.empty((len(self.numels), 5), dtype=np.int64)
+        arr[:, :4] = np.asarray(rows, dtype=np.int64).reshape(len(self.numels), 4)
+        arr[:, 4] = self.numels
+        self.dev.copy_(torch.from_numpy(arr), non_blocking=True)
         return self.dev
 
 

@@ -126,3 +126,22 @@ def test_experiment_config_loading(tmp_path):
     assert b.device == "cuda:1"
     b.model = object()                       # runtime objects are assigned onto the same mapping (run.py:23-29 usage)
     assert "model" in b
+
+
+def test_optimiser_pointer_tables_layout():
+    """device tables of the multi-tensor optimiser kernels: 40-byte records {p, g, m, v, numel} and 16-byte chunk
+    records {tensor, start} covering every element exactly once (built on the CPU here)"""
+    from onssen_b200 import _lib
+    numels = [5, _lib.OPT_CHUNK, _lib.OPT_CHUNK + 1, 3 * _lib.OPT_CHUNK]
+    tb = _lib.OptTables(numels, "cpu")
+    rows = [(1000 + i, 2000 + i, 3000 + i, 4000 + i) for i in range(len(numels))]
+    dev = tb.fill(rows)
+    assert dev.shape == (4, 5) and dev.dtype == torch.int64
+    assert dev[:, :4].tolist() == [list(r) for r in rows] and dev[:, 4].tolist() == numels
+    ch = tb.chunks.tolist()
+    assert tb.nchunks == len(ch) == 1 + 1 + 2 + 3
+    covered = {i: 0 for i in range(len(numels))}
+    for t, start in ch:
+        assert start % _lib.OPT_CHUNK == 0 and start < numels[t]
+        covered[t] += min(_lib.OPT_CHUNK, numels[t] - start)
+    assert [covered[i] for i in range(len(numels))] == numels
