@@ -145,3 +145,33 @@ def test_optimiser_pointer_tables_layout():
         assert start % _lib.OPT_CHUNK == 0 and start < numels[t]
         covered[t] += min(_lib.OPT_CHUNK, numels[t] - start)
     assert [covered[i] for i in range(len(numels))] == numels
+
+
+def test_host_index_arithmetic_properties():
+    """property tests of the integer host logic: rank shards tile the item range exactly; the crop-start bound of the
+    loaders equals the oracle's (wsj0_2mix.py:118-128 tiling rule) for any length / hop / frame_length"""
+    from hypothesis import given, settings, strategies as st
+    from onssen_b200.data.feature_utils import num_crop_starts
+    from onssen_b200.utils.dist import shard_range
+    from oracle import onssen_oracle as O
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 16))
+    def shards(n, world):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1 and all(s >= 0 for s in sizes)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(200, 200000), st.sampled_from([16, 64, 128, 256, 441]), st.integers(1, 600))
+    def crops(nsample, hop, T):
+        n = num_crop_starts(nsample, hop, T)
+        assert n == O.num_crop_starts(nsample, hop, T) and n >= 1
+        frames = 1 + nsample // hop
+        tiled = frames if frames > T else frames * (T // frames + 1)
+        assert n == tiled - T                       # np.random.randint(n) -> start in [0, n-1], crop always fits
+
+    shards()
+    crops()
