@@ -45,6 +45,20 @@ def _read_wav(fn, sampling_rate):
     return x
 
 
+def shard_files(files, rank, world_size, batch_size):
+    """Rank's share of a sorted file list for one-process-per-GPU runs.  With world_size > 1 the list is first
+    wrap-padded (files from the start are repeated) to a multiple of world_size * batch_size, so that EVERY rank runs
+    the same number of steps with the same batch size: a rank with one step more would issue gradient all-reduces
+    nobody answers (a silent NCCL hang), and cross-rank BatchNorm statistics assume equal per-rank row counts."""
+    if world_size <= 1:
+        return list(files)
+    if not files:
+        return []
+    unit = world_size * batch_size
+    padded = list(files) + [files[i % len(files)] for i in range((-len(files)) % unit)]
+    return padded[rank::world_size]
+
+
 def _opt(feature_options, key):
     return feature_options[key] if isinstance(feature_options, dict) else getattr(feature_options, key)
 
@@ -62,7 +76,7 @@ class _WavBatchLoader:
         self.shuffle = shuffle
         full_path = _opt(feature_options, "data_path") + "/wav8k/min/" + partition + "/mix/*.wav"
         files = sorted(glob.glob(full_path))
-        self.file_list = files[rank::world_size]
+        self.file_list = shard_files(files, rank, world_size, batch_size)
 
     def __len__(self):
         return (len(self.file_list) + self.batch_size - 1) // self.batch_size

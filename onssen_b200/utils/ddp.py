@@ -17,21 +17,33 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.pending = []
         self.bytes_reduced = 0
+        self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
 
     def reduce_bucket(self, grads):
-        """grads: dict name -> tensor (final). Launches one async all-reduce over the flattened bucket."""
+        """grads: dict name -> tensor (final).  NCCL: ONE grouped launch of in-place AVG all-reduces over the bucket's
+        tensors (ncclGroupStart/End through torch's coalescing manager): no flatten copy, no copy-back, no divide pass.
+        Other backends (gloo in the CPU tests): flatten, SUM, and write the average back in wait()."""
         if self.world == 1 or not grads:
             return
         names = sorted(grads)
-        flat = torch.cat([grads[n].reshape(-1) for n in names])
+        tensors = [grads[n] for n in names]
+        self.bytes_reduced += sum(t.numel() * t.element_size() for t in tensors)
+        if self.nccl:
+            with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+            self.pending.append((cm, None, names, grads))
+            return
+        flat = torch.cat([t.reshape(-1) for t in tensors])
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.pending.append((work, flat, names, grads))
-        self.bytes_reduced += flat.numel() * flat.element_size()
 
     def wait(self):
-        """Blocks until every bucket is reduced and writes the rank-averaged values back in place."""
+        """Blocks (the stream, for NCCL) until every bucket is reduced; afterwards the tensors hold the rank average."""
         for work, flat, names, grads in self.pending:
             work.wait()
+            if flat is None:
+                continue
             off = 0
             for n in names:
                 g = grads[n]
@@ -45,8 +57,10 @@ def broadcast_parameters(model, src=0):
     """Start every rank from rank `src`'s parameters and buffers."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
-    for t in list(model.parameters()) + list(model.buffers()):
-        dist.broadcast(t.data, src)
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.detach(), src)
+            torch.autograd.graph.increment_version(t)     # packed fp16 weight caches key on (data_ptr, _version)
 
 
 def enable_sync_batchnorm(model, on=True):
@@ -58,3 +72,15 @@ def enable_sync_batchnorm(model, on=True):
         if hasattr(m, "bn"):
             m.sync_bn = bool(on)
     return model
+
+
+def enable_global_loss_mean(on=True):
+    """Make `torch.mean(loss_dc(...))` (and the chimera / phase losses built on it) on every rank contribute to the
+    GLOBAL-batch scalar of the single-device arithmetic: the reference's (B,B) mean is mean_i(sum m_i) * mean_j(l_j)
+    (loss_dc.py:44 + train.py:79), a product of two batch means, so the average of per-rank products is not the product
+    of global means.  With this on, `loss_dc` all-reduces one scalar (sum_i sum m_i, plus the batch size) in its
+    forward and uses the global mean for the first factor: the rank-average of the per-rank scalars, and of the
+    gradients GradSync averages, is then exactly the full-batch value.  The trainer turns it on under torch.distributed."""
+    import importlib
+    # (`onssen_b200.loss.loss_dc` the attribute is the function, like in the reference package; get the module)
+    importlib.import_module("onssen_b200.loss.loss_dc").GLOBAL_MEAN[0] = bool(on)

@@ -2,7 +2,7 @@
 egs/wsj0-2mix/{deep_clustering,chimera}/evaluate.py.  mask x mixture STFT -> waveform runs on the device
 (onssen_istft_masked) and so does the VAD + K-means on the active-bin embeddings (onssen_kmeans_masks: Lloyd with a
 deterministic seeding instead of sklearn's RNG-driven k-means++; same partition up to the label order, which the
-permutation-invariant SI-SDR ignores).  SI-SDR is a few lines of torch (sdr.py is out of scope)."""
+permutation-invariant SI-SDR ignores)."""
 import itertools
 import os
 
@@ -12,19 +12,28 @@ from .. import _lib
 from .basic import AverageMeter
 
 
-def batch_si_sdr(est, ref):
-    """Permutation-invariant SI-SDR in dB (behaviour of onssen/evaluate/sdr.py:40-87). est/ref (B,S,n)."""
-    est = est.double() - est.double().mean(-1, keepdim=True)
-    ref = ref.double() - ref.double().mean(-1, keepdim=True)
-    S = est.shape[1]
-    best = None
-    for perm in itertools.permutations(range(S)):
-        e = est[:, list(perm)]
-        proj = (e * ref).sum(-1, keepdim=True) / (ref * ref).sum(-1, keepdim=True).clamp_min(1e-12) * ref
-        sdr = 10 * torch.log10((proj ** 2).sum(-1) / ((e - proj) ** 2).sum(-1).clamp_min(1e-12))
-        val = sdr.mean(1)
-        best = val if best is None else torch.maximum(best, val)
-    return float(best.mean().item())
+def batch_si_sdr(est, ref, return_perm=False):
+    """`batch_SDR_torch` of onssen/evaluate/sdr.py:40-87 restated for the device (pinned by tests/golden/sdr.npz,
+    generated from the live function): zero-mean both, SDR[i,j] of estimate i against reference j with the
+    reference's 1e-8 regularisers (sdr.py:24-32), best sum over source permutations (sorted order, first maximum
+    wins, sdr.py:71-82), divided by the number of sources.  est/ref (B,S,n) -> (B,) in the promoted dtype."""
+    dt = torch.promote_types(est.dtype, ref.dtype)
+    est, ref = est.to(dt), ref.to(dt)
+    B, S, n = est.shape
+    assert ref.shape == est.shape, "Estimation and original sources should have same shape."
+    assert S < n, "Axis 1 should be the number of sources, and axis 2 should be the signal."
+    est = est - est.mean(2, keepdim=True)
+    ref = ref - ref.mean(2, keepdim=True)
+    e, o = est[:, :, None, :], ref[:, None, :, :]                      # (B,S,1,n) x (B,1,S,n)
+    origin_power = (o * o).sum(-1, keepdim=True) + 1e-8
+    est_true = (o * e).sum(-1, keepdim=True) / origin_power * o
+    est_res = e - est_true
+    sdr = 10 * torch.log10((est_true ** 2).sum(-1) + 1e-8) - 10 * torch.log10((est_res ** 2).sum(-1) + 1e-8)   # (B,S,S)
+    perms = sorted(set(itertools.permutations(range(S))))
+    idx = torch.arange(S, device=est.device)
+    per = torch.stack([sdr[:, idx, torch.tensor(p, device=est.device)].sum(1) for p in perms], 1)      # (B, S!)
+    best, which = per.max(1)
+    return (best / S, which) if return_perm else best / S
 
 
 class tester:
@@ -54,7 +63,8 @@ class tester:
             for input, label in self.test_loader:
                 output = self.model(input)
                 sig_est, sig_ref = self.get_est_sig(input, label, output)
-                sdrs.update(batch_si_sdr(sig_est, sig_ref))
+                sdr = batch_si_sdr(sig_est, sig_ref)                          # (B,) like batch_SDR_torch
+                sdrs.update(float(sdr.mean().item()), sdr.numel())
         return sdrs.avg
 
 

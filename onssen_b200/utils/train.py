@@ -42,8 +42,9 @@ class trainer:
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         if self.world > 1:
-            from .ddp import GradSync, broadcast_parameters
+            from .ddp import GradSync, broadcast_parameters, enable_global_loss_mean
             broadcast_parameters(self.model)
+            enable_global_loss_mean(True)
             if getattr(self.model, "grad_sync", None) is None:
                 self.model.grad_sync = GradSync()
             self.verbose = self.verbose and self.rank == 0
@@ -65,7 +66,8 @@ class trainer:
             self.train(epoch)
             self.validate(epoch)
             if self.early_stop_count == 8:
-                print("Model stops improving, stop the training")
+                if self.verbose:
+                    print("Model stops improving, stop the training")
                 break
         if self.verbose:
             print("Model training is finished.")

@@ -6,11 +6,12 @@ onssen/utils/train.py:1) -- they contain no arithmetic and nothing below touches
 Fixtures pin: nn.deep_clustering / nn.chimera / nn.enhance forward (eval and train-mode BN) and
 loss.loss_dc / loss_chimera_msa / loss_chimera_psa / loss_mask_msa / loss_mask_psa.
 
-Usage:  python oracle/make_golden.py
+feat_*.npz pin the featurizer helpers (rows a2-a7) and sdr.npz pins SI-SDR, both from the live reference too.
+
+Usage:  python oracle/make_golden.py [--only models|phase|feat|sdr]
 """
 import os
 import sys
-import types
 
 import numpy as np
 
@@ -18,13 +19,9 @@ REF = "/root/reference"
 
 
 def import_reference():
-    for m in ["librosa", "librosa.core", "librosa.feature", "attrdict"]:
-        sys.modules.setdefault(m, types.ModuleType(m))
-    sys.modules["attrdict"].AttrDict = dict
-    sys.dont_write_bytecode = True
-    sys.path.insert(0, REF)
-    import onssen  # noqa
-    return onssen
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import ref_loader
+    return ref_loader.import_reference()
 
 
 def sd_to_np(sd):
@@ -144,46 +141,13 @@ def main_phase():
     live reference chimera + loss_dc: they pin our CUDA path and the numpy oracle to each other and to torch autograd,
     not to the (non-running) reference -> "parity unpinned" for these two rows."""
     import torch
-    import torch.nn.functional as Fn
     onssen = import_reference()
     out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
     torch.manual_seed(20260925)
     rng = np.random.RandomState(11)
 
-    class PhaseNetRepaired(torch.nn.Module):
-        def __init__(self, F, H, L, D):
-            super().__init__()
-            self.rnn = torch.nn.LSTM(3 * F, H, L, dropout=0.0, bidirectional=True, batch_first=True)
-            self.bn = torch.nn.BatchNorm1d(2 * H)
-            self.fc_phase = torch.nn.Linear(2 * H, 2 * F)         # repair: output_dim := num_speaker * input_dim
-            self.chimera = onssen.nn.chimera(F, H, L, D, dropout=0.0)
-
-        def forward(self, inp):
-            x_mag, x_phase = inp
-            emb, m_a, m_b = self.chimera([x_mag])
-            B, T, F = m_a.shape
-            outs, self.pre_norms = [], []
-            for m in (m_a, m_b):
-                y, _ = self.rnn(torch.cat((x_mag * m, x_phase.reshape(B, T, -1)), 2))
-                y = self.bn(y.permute(0, 2, 1)).permute(0, 2, 1)
-                v = self.fc_phase(y).reshape(B, T, F, -1) + x_phase
-                self.pre_norms.append(v.detach().norm(dim=-1))   # conditioning of the normalisation, for the tests
-                outs.append(Fn.normalize(v, p=2, dim=-1))
-            return [emb, m_a, m_b] + outs
-
-    def loss_phase_repaired(output, label):
-        emb, m_a, m_b, p_a, p_b = output                           # repair: 5 outputs
-        oh, mix, s1, s2, ph1, ph2 = label
-        B = mix.shape[0]
-        l_emb = onssen.loss.loss_dc([emb], [oh, mix])              # repair: mag_mix belongs to the label list
-        l1n = lambda x: x.abs().reshape(B, -1).sum(1)
-        lm1 = l1n(m_a * mix - s1) + l1n(m_b * mix - s2)
-        lm2 = l1n(m_b * mix - s1) + l1n(m_a * mix - s2)
-        cs = lambda a, b: Fn.cosine_similarity(a, b, dim=3)
-        lp1 = (-mix * cs(p_a, ph1) - mix * cs(p_b, ph2)).reshape(B, -1).sum(1)
-        lp2 = (-mix * cs(p_b, ph1) - mix * cs(p_a, ph2)).reshape(B, -1).sum(1)
-        first = lm1 < lm2
-        return l_emb * 0.975 + torch.where(first, lm1, lm2) * 0.025 + torch.where(first, lp1, lp2) * 0.025
+    from oracle.phase_repaired import build as build_phase
+    PhaseNetRepaired, loss_phase_repaired = build_phase(onssen)
 
     cases = {"small": dict(B=3, T=16, F=9, H=8, L=2, D=4), "mid": dict(B=2, T=24, F=33, H=40, L=2, D=20)}
     for name, c in cases.items():
@@ -212,8 +176,75 @@ def main_phase():
         print("wrote phase", name)
 
 
+class _Opts(dict):
+    __getattr__ = dict.__getitem__
+
+
+def main_feat():
+    """Rows a2-a7: the reference's OWN `wsj0_2mix_dataset.get_feature` (onssen/data/wsj0_2mix.py:103-158: tile,
+    np.random crop, get_log_magnitude, np.abs, get_one_hot + VAD, get_cos_difference, get_phase) run live on synthetic
+    waveforms.  The only substituted piece is `get_stft` (librosa, absent) -> oracle.stft of the in-memory signal
+    (oracle/ref_loader.patch_stft).  Stored: waveforms, the numpy seed, the crop start the reference drew, and every
+    returned tensor, for the 256/64 case (frames > frame_length) and the 1024/256 tiling case (frames <= frame_length)."""
+    import torch  # noqa: F401
+    onssen = import_reference()
+    from oracle import ref_loader, onssen_oracle as O
+    out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+    cases = {"crop": dict(nsample=6400, n_fft=256, hop=64, T=60, seed=314),        # 101 frames -> crop 60
+             "tile": dict(nsample=7000, n_fft=1024, hop=256, T=40, seed=2718)}     # 28 frames <= 40 -> tile x2 -> crop
+    for name, c in cases.items():
+        mix, s1, s2 = O.synth_utterance(4000 + c["seed"], c["nsample"])
+        sigs = {"/x/mix/u.wav": mix, "/x/s1/u.wav": s1, "/x/s2/u.wav": s2}
+        ref_loader.patch_stft(onssen, sigs)
+        out = dict(mix=mix, s1=s1, s2=s2, cfg=np.array([c["nsample"], c["n_fft"], c["hop"], c["T"], c["seed"]]))
+        got = {}
+        for model_name in ("dc", "chimera", "chimera++", "phase"):
+            opts = _Opts(data_path="/nonexistent", batch_size=1, frame_length=c["T"], sampling_rate=8000,
+                         window_size=c["n_fft"], hop_size=c["hop"], db_threshold=40)
+            ds = onssen.data.wsj0_2mix.wsj0_2mix_dataset(model_name, opts, "tr")
+            np.random.seed(c["seed"])
+            inp, lab = ds.get_feature("/x/mix/u.wav")
+            got[model_name] = ([t.numpy() for t in inp], [t.numpy() for t in lab])
+        # the four label layouts share their leading entries (wsj0_2mix.py:137-152): store each array once
+        full_in, full_lab = got["chimera++"]
+        same = lambda a, b: a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+        assert len(got["dc"][1]) == 2 and len(got["chimera"][1]) == 4 and len(got["phase"][1]) == 6
+        assert all(same(a, b) for a, b in zip(got["dc"][1], full_lab[:2])) and same(got["dc"][0][0], full_in[0])
+        assert all(same(a, b) for a, b in zip(got["chimera"][1], full_lab[:4]))
+        assert all(same(a, b) for a, b in zip(got["phase"][1][:4], full_lab[:4])) and same(got["phase"][0][0], full_in[0])
+        for k, a in zip(("feature", "one_hot", "mag_mix", "mag_s1", "mag_s2", "cos_s1", "cos_s2"), full_in + full_lab):
+            out[k] = a
+        out["phase_mix"], out["phase_s1"], out["phase_s2"] = got["phase"][0][1], got["phase"][1][4], got["phase"][1][5]
+        np.random.seed(c["seed"])
+        out["crop_start"] = np.array(np.random.randint(O.num_crop_starts(c["nsample"], c["hop"], c["T"])))
+        np.savez_compressed(os.path.join(out_dir, f"feat_{name}.npz"), **out)
+        print("wrote feat", name, "crop_start", int(out["crop_start"]))
+
+
+def main_sdr():
+    """batch_SDR_torch (onssen/evaluate/sdr.py:40-87) on seeded signals: pins utils.test.batch_si_sdr."""
+    import torch
+    onssen = import_reference()
+    out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+    rng = np.random.RandomState(99)
+    B, S, n = 5, 2, 2000
+    ref = rng.standard_normal((B, S, n)).astype(np.float32)
+    est = ref[:, ::-1].copy() * rng.uniform(0.3, 2, (B, S, 1)).astype(np.float32)
+    est[::2] = ref[::2]                                     # some batches un-permuted
+    est += rng.standard_normal((B, S, n)).astype(np.float32) * rng.uniform(0.01, 1.0, (B, 1, 1)).astype(np.float32)
+    sdr, perm = onssen.evaluate.batch_SDR_torch(torch.from_numpy(est), torch.from_numpy(ref), return_perm=True)
+    np.savez_compressed(os.path.join(out_dir, "sdr.npz"), est=est, ref=ref, sdr=sdr.numpy(), perm=perm.numpy())
+    print("wrote sdr", sdr.numpy())
+
+
 if __name__ == "__main__":
-    # `--only phase` regenerates just the phase fixtures (the others are seeded independently and stay bit-identical)
-    if sys.argv[1:] != ["--only", "phase"]:
+    # `--only X` regenerates one family (each is seeded independently, the others stay bit-identical)
+    only = sys.argv[2] if sys.argv[1:2] == ["--only"] else None
+    if only in (None, "models"):
         main()
-    main_phase()
+    if only in (None, "phase"):
+        main_phase()
+    if only in (None, "feat"):
+        main_feat()
+    if only in (None, "sdr"):
+        main_sdr()

@@ -57,8 +57,32 @@ def _worker(rank, world, port, ret):
     lin = torch.nn.Linear(3, 2)
     with torch.no_grad():
         lin.weight.fill_(float(rank))
+    v0 = lin.weight._version
     broadcast_parameters(lin, 0)
     assert float(lin.weight.abs().max()) == 0.0
+    assert lin.weight._version > v0                   # packed-weight caches keyed on _version see the broadcast
+    # exact data-parallel coupling of the (B,B) loss mean (utils.ddp.enable_global_loss_mean): with the first factor
+    # replaced by its global mean, the rank-average of mean(loss_bb) is the single-device value and the rank-averaged
+    # gradient coefficient of l_j is (sum m / n) / n
+    import importlib
+    from onssen_b200.utils.ddp import enable_global_loss_mean
+    LD = importlib.import_module("onssen_b200.loss.loss_dc")
+    enable_global_loss_mean(True)
+    assert LD.GLOBAL_MEAN[0]
+    nloc = 6
+    l_loc = l_all[rank * nloc:(rank + 1) * nloc].clone().requires_grad_(True)
+    m_loc = m_all[rank * nloc:(rank + 1) * nloc]
+    mbar = LD._global_first_factor(m_loc)
+    want_mbar = float(m_all[:world * nloc].double().mean())
+    assert abs(float(mbar) - want_mbar) < 1e-5 * want_mbar
+    per_rank = ((mbar * l_loc).unsqueeze(0).expand(nloc, nloc)).mean()
+    per_rank.backward()
+    tot = per_rank.detach().clone().double()
+    dist.all_reduce(tot)
+    la, ma = l_all[:world * nloc].double(), m_all[:world * nloc].double()
+    assert abs(float(tot) / world - float((la[None, :] * ma[:, None]).mean())) < 1e-6 * float(tot)
+    assert torch.allclose(l_loc.grad / world, torch.full((nloc,), want_mbar / (world * nloc)), rtol=1e-5)
+    LD.GLOBAL_MEAN[0] = False
     # rank-aware trainer: parameters broadcast from rank 0, validation loss averaged over ranks (identical early-stop
     # decisions), only rank 0 writes the checkpoint.  A torch-only stand-in model: the trainer is model-agnostic.
     from onssen_b200.utils import AttrDict, trainer
@@ -120,8 +144,18 @@ def test_loader_file_sharding(tmp_path):
               db_threshold=40)
     full = wsj0_2mix_dataloader("dc", fo, "tr")
     assert len(full.file_list) == 5 and len(full) == 3
-    parts = [wsj0_2mix_dataloader("dc", fo, "tr", rank=r, world_size=2).file_list for r in range(2)]
-    assert sorted(parts[0] + parts[1]) == full.file_list and not set(parts[0]) & set(parts[1])
+    loaders = [wsj0_2mix_dataloader("dc", fo, "tr", rank=r, world_size=2) for r in range(2)]
+    parts = [ld.file_list for ld in loaders]
+    # 5 files, 2 ranks x batch 2: wrap-padded to 8 so that both ranks run the SAME number of full batches (a rank with an
+    # extra step would issue all-reduces nobody answers); every file is still covered
+    assert set(parts[0] + parts[1]) == set(full.file_list) and len(parts[0]) == len(parts[1]) == 4
+    assert len(loaders[0]) == len(loaders[1]) == 2
+    from onssen_b200.data.wsj0_2mix import shard_files
+    for n, world, bs in [(0, 2, 4), (1, 4, 3), (7, 2, 2), (8, 2, 2), (33, 8, 4), (5, 1, 2)]:
+        files = [f"f{i}" for i in range(n)]
+        sh = [shard_files(files, r, world, bs) for r in range(world)]
+        assert len({len(x) for x in sh}) == 1 and (world == 1 or len(sh[0]) % bs == 0)
+        assert set(sum(sh, [])) == set(files)
     (mix, s1, s2), lengths = full._load(full.file_list[:2])
     assert mix.shape == (2, 4100) and lengths.tolist() == [4000, 4100]
     assert float(mix[0, 4000:].abs().max()) == 0.0           # zero padded to the batch pitch

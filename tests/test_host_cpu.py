@@ -175,3 +175,22 @@ def test_host_index_arithmetic_properties():
 
     shards()
     crops()
+
+
+def test_batch_si_sdr_matches_reference_fixture():
+    """tests/golden/sdr.npz = the live batch_SDR_torch(est, ref, return_perm=True) (onssen/evaluate/sdr.py:40-87)."""
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from onssen_b200.utils.test import batch_si_sdr
+    _, g = load_golden("sdr.npz")
+    sdr, perm = batch_si_sdr(torch.from_numpy(g["est"]), torch.from_numpy(g["ref"]), return_perm=True)
+    assert sdr.dtype == torch.float32 and sdr.shape == (5,)
+    np.testing.assert_allclose(sdr.numpy(), g["sdr"], atol=2e-4)
+    np.testing.assert_array_equal(perm.numpy(), g["perm"])
+    # three sources: permutation search against brute force in float64
+    rng = np.random.RandomState(0)
+    ref = torch.from_numpy(rng.standard_normal((2, 3, 500)))
+    est = ref[:, [2, 0, 1]] + 0.1 * torch.from_numpy(rng.standard_normal((2, 3, 500)))
+    sdr3, p3 = batch_si_sdr(est, ref, return_perm=True)
+    assert sdr3.dtype == torch.float64 and (sdr3 > 15).all() and (p3 == p3[0]).all()

@@ -144,3 +144,48 @@ def test_oracle_clip_adam_matches_torch():
         assert abs(n - tn) < 1e-4 * tn
         for a, t in zip(ps, tp):
             assert np.abs(a - t.detach().numpy()).max() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ rows a2-a7
+@pytest.mark.parametrize("name", ["crop", "tile"])
+def test_oracle_featurizer_bit_exact_vs_reference_get_feature(name):
+    """feat_*.npz come from the reference's OWN wsj0_2mix_dataset.get_feature (oracle/make_golden.py:main_feat; only
+    get_stft is substituted).  Integer work (crop index, tiling, labels, VAD) AND the float helpers must match
+    bit for bit, dtype included."""
+    _, g = load_golden(f"feat_{name}.npz")
+    nsample, n_fft, hop, T, seed = (int(v) for v in g["cfg"])
+    np.random.seed(seed)
+    start = np.random.randint(O.num_crop_starts(nsample, hop, T))          # wsj0_2mix.py:125
+    assert start == int(g["crop_start"])
+    inp, lab = O.featurize(g["mix"], g["s1"], g["s2"], n_fft, hop, T, start, 40, "chimera++")
+    for k, a in zip(("feature", "one_hot", "mag_mix", "mag_s1", "mag_s2", "cos_s1", "cos_s2"), inp + lab):
+        assert a.dtype == g[k].dtype and a.shape == g[k].shape, k
+        np.testing.assert_array_equal(a, g[k], err_msg=k)
+    inp, lab = O.featurize(g["mix"], g["s1"], g["s2"], n_fft, hop, T, start, 40, "phase")
+    for k, a in zip(("feature", "phase_mix", "one_hot", "mag_mix", "mag_s1", "mag_s2", "phase_s1", "phase_s2"), inp + lab):
+        assert a.dtype == g[k].dtype and a.shape == g[k].shape, k
+        np.testing.assert_array_equal(a, g[k], err_msg=k)
+    for model_name, n_lab in (("dc", 2), ("chimera", 4)):
+        inp, lab = O.featurize(g["mix"], g["s1"], g["s2"], n_fft, hop, T, start, 40, model_name)
+        assert len(inp) == 1 and len(lab) == n_lab
+    assert (g["one_hot"].sum(-1) == 0).any() and (g["one_hot"].sum(-1) == 1).any()      # the VAD actually bites
+    if name == "tile":
+        frames = 1 + nsample // hop
+        assert frames <= T                                                            # the tiling branch ran
+        np.testing.assert_array_equal(g["mag_mix"][frames - start], g["mag_mix"][0] if start == 0 else
+                                      np.abs(O.stft(g["mix"], n_fft, hop))[0])
+
+
+def test_staged_reference_is_unmodified():
+    """oracle/_ref (when staged) holds the reference's files byte for byte (sha256 manifest written at staging time)."""
+    import hashlib, json, os
+    from oracle import ref_loader
+    root = ref_loader.REF_STAGED
+    if not os.path.isdir(root):
+        pytest.skip("oracle/_ref not staged")
+    man = json.load(open(os.path.join(root, "MANIFEST.json")))["sha256"]
+    assert "onssen/nn/deep_clustering.py" in man and "onssen/loss/loss_dc.py" in man
+    for rel, h in man.items():
+        assert hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest() == h, rel
+        if os.path.isfile(os.path.join("/root/reference", rel)):
+            assert open(os.path.join("/root/reference", rel), "rb").read() == open(os.path.join(root, rel), "rb").read()
