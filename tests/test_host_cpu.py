@@ -69,23 +69,30 @@ def test_attrdict_and_optimizer_shims():
     assert ob.data.num_crop_starts(32000, 64, 400) == 101
 
 
-def test_bench_reference_arm_line_contract(monkeypatch, capsys):
-    """`bench.py --impl reference` (the oracle port on the host cores) on a shrunken workload: one JSON line with the
-    keys the driver reads."""
+@pytest.mark.parametrize("staged", [True, False])
+def test_bench_reference_arm_line_contract(monkeypatch, capsys, staged):
+    """`bench.py --impl reference` on a shrunken workload: one JSON line with the keys the driver reads.  With
+    oracle/_ref staged the arm runs the reference's own torch modules (kind "reference", same config as the GPU arm);
+    without it, the numpy oracle port (kind "port")."""
     import argparse
     import json
     import bench
-    monkeypatch.setitem(bench.CFG, "H", 8)
-    monkeypatch.setitem(bench.CFG, "L", 1)
-    monkeypatch.setitem(bench.CFG, "D", 4)
-    monkeypatch.setitem(bench.CFG, "T", 20)
-    monkeypatch.setitem(bench.CFG, "nsample", 7680)    # 121 frames: crop starts < 101 stay valid at T=20
+    from oracle import ref_loader
+    if staged and not ref_loader.available():
+        pytest.skip("oracle/_ref not staged")
+    if not staged:
+        monkeypatch.setattr(ref_loader, "available", lambda: False)
+    monkeypatch.setitem(bench.CFG, "margs", (129, 8, 1, 4))
+    monkeypatch.setitem(bench.CFG, "B", 3)
+    monkeypatch.setattr(bench, "T_FRAMES", 20)
+    monkeypatch.setitem(bench.CFG, "nsample", 7680)
     monkeypatch.delenv("RANK", raising=False)
     bench.run_reference(argparse.Namespace(steps=1, warmup=0, gpus=1))
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "utterances/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert line["same_config"] is staged and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["metric"] == bench.METRIC
 
