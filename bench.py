@@ -233,6 +233,10 @@ def build_workload(ob, wl, dev, dropout=None):
     return model, featurize, loss_fn
 
 
+def _scalar(x):
+    return float(x.detach()) if hasattr(x, "detach") else float(x)
+
+
 def event_ms(torch, fn, n, barrier):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,7 +288,7 @@ def time_workload(torch, ob, wl, dev, rank, world, barrier, K, W, grad_sync=None
     out = {"workload": wl["desc"], "batch_per_gpu": B, "steps": K,
            "fwd_loss_ms": t[0].item() / K, "fwd_loss_utt_s": world * B * K / (t[0].item() / 1e3),
            "train_ms": t[1].item() / K, "train_utt_s": world * B * K / (t[1].item() / 1e3),
-           "loss_fwd": float(lf), "loss_train": float(lt)}
+           "loss_fwd": _scalar(lf), "loss_train": _scalar(lt)}
     del model, opt, batches
     torch.cuda.empty_cache()
     return out
@@ -341,7 +345,7 @@ def time_gpu_reference(torch, dev, ob, dev_batches, K, W):
            "train_ms": ms_t / K, "train_utt_s": B * K / (ms_t / 1e3), "steps": K,
            "allow_tf32": {"cudnn": bool(torch.backends.cudnn.allow_tf32),
                           "matmul": bool(torch.backends.cuda.matmul.allow_tf32)},
-           "loss_fwd": float(lf), "loss_train": float(lt)}
+           "loss_fwd": _scalar(lf), "loss_train": _scalar(lt)}
     del model, opt, feats
     torch.cuda.empty_cache()
     return out

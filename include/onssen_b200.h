@@ -143,6 +143,7 @@ void onssen_blstm_rec_set_trace(void* device_buf_64_int64);
 /* Tuning knob: SM cycles every CTA waits between publishing h_t and its first gather round (default tuned on B200). */
 void onssen_blstm_rec_set_poll_delay(int cycles);
 
+
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm1d over (B,T) per channel (replaces permute + nn.BatchNorm1d + permute,
  * deep_clustering.py:36-38, enhancement.py:45-47).
@@ -249,9 +250,12 @@ void onssen_blstm_rec_bwd_set_persistent(int on);
 /* debug: clock64 stamps of CTA 0 of the persistent BPTT kernel, steps 100..107, [step][slot 0..7][warp 0..7]
    (512 int64); NULL = off */
 void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64);
+/* sat_count_u32 (optional, device uint32, accumulated): how many published dG values did not fit the flag range of
+ * the persistent kernel (|dG*scale| >= 2, or NaN) and were clamped -- an exploding recurrent gradient must not be
+ * silent (the trainer reads it at its logging interval). */
 int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
-                         void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
-                         unsigned long long seed, unsigned long long offset, void* stream);
+                         void* scratch, const float* scale2, void* sat_count_u32, int B, int T, int H,
+                         float dropout_p, unsigned long long seed, unsigned long long offset, void* stream);
 
 /* Backward of onssen_loss_pit_l1_fwd w.r.t. the two masks (g [B] = upstream gradient, perm from the forward);
  * d_mask_a / d_mask_b dense [B][N]. */

@@ -78,7 +78,7 @@ _SIGNATURES = {
     "onssen_loss_phase_cos_bwd": (c_int, [c_vp] * 7 + [c_int] * 2 + [c_vp] * 3),
     "onssen_l2norm_pairs_bwd": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_vp] * 3),
     "onssen_phase_input_bwd": (c_int, [c_vp, c_ll, c_vp] + [c_int] * 5 + [c_vp] * 2),
-    "onssen_blstm_rec_bwd": (c_int, [c_vp] * 7 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
+    "onssen_blstm_rec_bwd": (c_int, [c_vp] * 8 + [c_int, c_int, c_int, c_f, c_ull, c_ull, c_vp]),
     "onssen_loss_pit_l1_bwd": (c_int, [c_vp, c_vp, c_ll] + [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_vp]),
     "onssen_sigmoid_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "onssen_add_inplace": (c_int, [c_vp, c_vp, c_ll, c_vp]),
@@ -580,11 +580,30 @@ def blstm_rec_fwd_train(gates, whh_p, B, T, H, y_h, y_f, c_out, h_raw, dropout_p
     _check(rc, "onssen_blstm_rec_fwd")
 
 
+_BPTT_SAT = {}     # device -> int32[1]: clamped dG values of the persistent BPTT kernel since the last read
+
+
+def bptt_saturation_count(device=None, reset=True):
+    """Number of BPTT exchange values that were clamped into the flag range since the last call (device -> host read:
+    call it at a logging interval, not every step).  Non-zero means the recurrent gradient exceeded 32x the largest
+    output gradient (or was NaN) and the step's gradient is not trustworthy."""
+    total = 0
+    for dev, t in _BPTT_SAT.items():
+        if device is None or torch.device(device) == dev:
+            total += int(t.item())
+            if reset:
+                t.zero_()
+    return total
+
+
 def blstm_rec_bwd(act_gates, dg16, c, dy, whh_t, scale2, B, T, H, dropout_p, seed, offset):
     lib = load()
     scratch = torch.empty(lib.onssen_blstm_rec_bwd_scratch_bytes(B, H), device=c.device, dtype=torch.uint8)
+    sat = _BPTT_SAT.get(c.device)
+    if sat is None:
+        sat = _BPTT_SAT[c.device] = torch.zeros(1, device=c.device, dtype=torch.int32)
     rc = lib.onssen_blstm_rec_bwd(_p(act_gates), _p(dg16), _p(c), _p(_req(dy, torch.float32)), _p(whh_t), _p(scratch),
-                                  _p(scale2), B, T, H, float(dropout_p), int(seed), int(offset), _stream())
+                                  _p(scale2), _p(sat), B, T, H, float(dropout_p), int(seed), int(offset), _stream())
     _check(rc, "onssen_blstm_rec_bwd")
 
 

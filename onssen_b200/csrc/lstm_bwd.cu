@@ -21,6 +21,7 @@ struct BwdParams {
   uint32_t* frag;       // dG of the last processed step in B-fragment order: [parity][dir][bb][kstep][ntile][lane][2]
   float* dc;            // [2][B][Hp] cell-gradient carry
   const float* scale2;  // {scale, 1/scale}
+  unsigned int* sat;    // optional: number of published values that had to be clamped into the flag range (or NaN)
   int B, T, H, Hp, s;
   float dropout_p;
   unsigned int seed_lo, seed_hi;
@@ -484,6 +485,10 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_persistent_kernel(const BwdPa
       if (valid_items & (1u << i)) {   // pad batch columns publish zeros so that every fragment entry turns fresh
         __half2 lo = __halves2half2(to_half_flag_range(s_i), to_half_flag_range(s_f));
         __half2 hi = __halves2half2(to_half_flag_range(s_g), to_half_flag_range(s_o));
+        // |x| >= 2 (or NaN: the comparison is false) cannot be represented next to the flag bit: the clamped value
+        // is published and the event is counted so that the host can surface it (never silent)
+        if (!(fmaxf(fmaxf(fabsf(s_i), fabsf(s_f)), fmaxf(fabsf(s_g), fabsf(s_o))) < 1.9995f) && p.sat != nullptr)
+          atomicAdd(p.sat, 1u);
         o.x = *reinterpret_cast<uint32_t*>(&lo);
         o.y = *reinterpret_cast<uint32_t*>(&hi);
       }
@@ -560,7 +565,8 @@ extern "C" size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H) {
 }
 
 extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
-                                    void* scratch, const float* scale2, int B, int T, int H, float dropout_p,
+                                    void* scratch, const float* scale2, void* sat_count_u32, int B, int T, int H,
+                                    float dropout_p,
                                     unsigned long long seed, unsigned long long offset, void* stream) {
   if (!act_gates || !dg16 || !c || !dy || !whh_t || !scratch || !scale2 || B <= 0 || T <= 0 || H <= 0)
     return ONSSEN_ERR_ARG;
@@ -568,7 +574,7 @@ extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c
   BwdParams p;
   p.actg = act_gates; p.dg16 = (__half*)dg16; p.c = c; p.dy = dy; p.wt = (const uint32_t*)whh_t; p.dc = dc_carry;
   p.frag = (uint32_t*)((uint8_t*)scratch + (size_t)2 * B * hp_of(H) * 4);
-  p.scale2 = scale2; p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H);
+  p.scale2 = scale2; p.sat = (unsigned int*)sat_count_u32; p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H);
   p.dropout_p = dropout_p;
   const unsigned long long mix = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
   p.seed_lo = (unsigned int)mix;

@@ -45,7 +45,10 @@ struct RecParams {
   __half* y_h;
   float* y_f;
   __half* hbuf;
-  unsigned int* flags;
+  // column-chunk launches only.  (These two replace an unused 8-byte field of the round-1 struct: growing the
+  // parameter struct changes ptxas' allocation and the NB=32 instantiation starts to spill.)
+  int Bp;                  // row pitch of the time-major buffers in utterances (> B for a column chunk)
+  unsigned int hash_off;   // element offset of the chunk's first column (dropout hash uses absolute indices)
   int B, T, H, Hp, nrb, S, Bs;
   float dropout_p;
   unsigned int seed_lo, seed_hi;
@@ -123,7 +126,9 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
   return v;
 }
 
-template <int NB, bool TC>
+// CHUNK: the launch covers a column chunk of a larger batch (row pitch p.Bp > p.B, absolute dropout indices); the
+// whole-batch instantiation keeps the round-1 register allocation (two more live parameters spill at NB = 32).
+template <int NB, bool TC, bool CHUNK>
 __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecParams p) {
   constexpr int NBP = NB <= 16 ? 16 : 32;  // MMA N / rows of the h operand tile
   constexpr int NBH = NB / 2;              // batch columns per gate-warp half
@@ -291,8 +296,8 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
       const int t1 = T > 1 ? (dir ? T - 2 : 1) : t0;
 #pragma unroll
       for (int j = 0; j < NBH; ++j) {
-        gpre[j] = __ldcs(gcol + ((long long)t0 * p.B + jcl[j]) * ldg);
-        gnext[j] = __ldcs(gcol + ((long long)t1 * p.B + jcl[j]) * ldg);
+        gpre[j] = __ldcs(gcol + ((long long)t0 * (CHUNK ? p.Bp : p.B) + jcl[j]) * ldg);
+        gnext[j] = __ldcs(gcol + ((long long)t1 * (CHUNK ? p.Bp : p.B) + jcl[j]) * ldg);
       }
     }
     if (!TC) mbar_wait(wbar, 0);
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
         xch[r * XP + jbase + j] = av;
         // in place: this element was consumed (prefetched) two steps ago
         if (p.act_out != nullptr && jbase + j < nb_valid)
-          p.act_out[((long long)t * p.B + b0 + jbase + j) * ldg + (long long)dir * 4 * Hp + rb * 128 + r] = av;
+          p.act_out[((long long)t * (CHUNK ? p.Bp : p.B) + b0 + jbase + j) * ldg + (long long)dir * 4 * Hp + rb * 128 + r] = av;
       }
       __syncwarp();
       if (tid == 0) REC_TRACE(10);
@@ -405,11 +410,11 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
       for (int ci = 0; ci < NBH / 4; ++ci) {
         const int j = jbase + 4 * ci + gate;
         if (j < nb_valid) {
-          const int m = t * p.B + b0 + j;
+          const int m = t * (CHUNK ? p.Bp : p.B) + b0 + j;
           const long long o = (long long)m * ldy + dir * Hp + u;
           float hv = hval[ci];
           if (p.dropout_p > 0.f) {
-            const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)o);
+            const float rnd = hash_uniform32(p.seed_lo, p.seed_hi, (unsigned int)o + (CHUNK ? p.hash_off : 0u));
             hv = rnd < p.dropout_p ? 0.f : hv * keep_scale;
           }
           if (p.y_h) p.y_h[o] = __float2half_rn(hv);
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
 #pragma unroll
         for (int j = 0; j < NBH; ++j) {
           gpre[j] = gnext[j];
-          gnext[j] = __ldcs(gcol + ((long long)tn * p.B + jcl[j]) * ldg);
+          gnext[j] = __ldcs(gcol + ((long long)tn * (CHUNK ? p.Bp : p.B) + jcl[j]) * ldg);
         }
       }
       if (s + 1 < T) {
@@ -483,7 +488,7 @@ size_t rec_smem_bytes(int Hp) {
 template <int NB, bool TC>
 int launch_rec(RecParams& p, int grid, cudaStream_t stream) {
   const size_t smem = rec_smem_bytes<NB, TC>(p.Hp);
-  auto kern = blstm_rec_kernel<NB, TC>;
+  auto kern = (p.Bp != p.B) ? blstm_rec_kernel<NB, TC, true> : blstm_rec_kernel<NB, TC, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return ONSSEN_ERR_CUDA;
   int per_sm = 0;
@@ -584,27 +589,46 @@ static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int
   if (!gates || !whh_p || !workspace || B <= 0 || T <= 0 || H <= 0) return ONSSEN_ERR_ARG;
   if (!y_h && !y_f) return ONSSEN_ERR_ARG;
   if (dropout_p < 0.f || dropout_p >= 1.f) return ONSSEN_ERR_ARG;
-  const SlicePlan sp = plan_slices(B, H);
-  if (!sp.ok) return ONSSEN_ERR_UNSUPPORTED;
+  // batches above one launch's capacity (32 columns x co-resident CTAs per row block: 96 utterances at H=600 on 148
+  // SMs) run as column chunks of nearly equal size, back to back on the stream (torch.nn.LSTM has no batch limit:
+  // deep_clustering.py:34-35)
+  const int Hp = hp_of(H);
+  const int smax = num_sms() / (2 * (Hp / 32));
+  if (smax < 1) return ONSSEN_ERR_UNSUPPORTED;
+  const int bmax = smax * 32;
+  const int nchunk = (B + bmax - 1) / bmax;
+  const int per = (B + nchunk - 1) / nchunk;
   RecParams p;
-  p.gates = gates;
   p.whh = (const __half*)whh_p;
-  p.y_h = (__half*)y_h;
-  p.y_f = y_f;
-  p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H); p.nrb = p.Hp / 32; p.S = sp.S; p.Bs = sp.Bs;
+  p.Bp = B; p.T = T; p.H = H; p.Hp = Hp; p.nrb = p.Hp / 32;
   p.dropout_p = dropout_p;
   const unsigned long long mix = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
   p.seed_lo = (unsigned int)mix;
   p.seed_hi = (unsigned int)(mix >> 32);
   p.trace = g_trace_ptr;
   p.poll_delay = g_poll_delay;
-  p.act_out = act_out; p.c_out = c_out; p.h_raw = (__half*)h_raw;
-  const size_t hbuf_bytes = (size_t)2 * 2 * sp.S * p.Hp * sp.NBP * 2;
-  if (workspace_bytes < 256 + hbuf_bytes) return ONSSEN_ERR_ARG;
-  p.flags = (unsigned int*)workspace;
   p.hbuf = (__half*)((uint8_t*)workspace + 256);
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(workspace, 0, 256 + hbuf_bytes, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
-  const int grid = 2 * sp.S * p.nrb;
-  return use_tensor_cores ? dispatch_nb<true>(sp.NB, p, grid, s) : dispatch_nb<false>(sp.NB, p, grid, s);
+  for (int c0 = 0; c0 < B; c0 += per) {
+    const int bc = (B - c0) < per ? (B - c0) : per;
+    const SlicePlan sp = plan_slices(bc, H);
+    if (!sp.ok) return ONSSEN_ERR_UNSUPPORTED;
+    // the chunk's first column is folded into the base pointers (row m = t*Bp + b: column offset = b rows)
+    const size_t og = (size_t)c0 * 8 * Hp, oy = (size_t)c0 * 2 * Hp;
+    p.gates = gates + og;
+    p.y_h = y_h ? (__half*)y_h + oy : nullptr;
+    p.y_f = y_f ? y_f + oy : nullptr;
+    p.act_out = act_out ? act_out + og : nullptr;
+    p.c_out = c_out ? c_out + oy : nullptr;
+    p.h_raw = h_raw ? (__half*)h_raw + oy : nullptr;
+    p.hash_off = (unsigned int)oy;
+    p.B = bc; p.S = sp.S; p.Bs = sp.Bs;
+    const size_t hbuf_bytes = (size_t)2 * 2 * sp.S * p.Hp * sp.NBP * 2;
+    if (workspace_bytes < 256 + hbuf_bytes) return ONSSEN_ERR_ARG;
+    if (cudaMemsetAsync(workspace, 0, 256 + hbuf_bytes, s) != cudaSuccess) return ONSSEN_ERR_CUDA;
+    const int grid = 2 * sp.S * p.nrb;
+    const int rc = use_tensor_cores ? dispatch_nb<true>(sp.NB, p, grid, s) : dispatch_nb<false>(sp.NB, p, grid, s);
+    if (rc != ONSSEN_OK) return rc;
+  }
+  return ONSSEN_OK;
 }

@@ -8,9 +8,9 @@
 //   get_cos_difference  feature_utils.py:67-80,  get_phase feature_utils.py:54-64
 //   get_one_hot         feature_utils.py:83-95
 //   masked istft        egs/wsj0-2mix/deep_clustering/evaluate.py:42-45, chimera/evaluate.py:40-43
-// One CTA per (frame, utterance) computes the mix/s1/s2 spectra together (radix-2 FFT in shared memory,
-// fp32) and writes every requested feature directly in the (B,T,F) layout the model consumes; only the
-// cropped T frames are ever computed.  HBM-bound (waveforms in, features out), FLOPs are negligible.
+// One warp per (frame, signal) computes a spectrum (half-length complex FFT in shared memory, fp32) and writes
+// every requested feature directly in the (B,T,F) layout the model consumes; only the cropped T frames are ever
+// computed.  HBM-bound (waveforms in, features out), FLOPs are negligible.
 #include "common.cuh"
 
 namespace onssen {
@@ -66,66 +66,128 @@ __global__ void fill_kernel(float* p, int n, float v) {
   if (i < n) p[i] = v;
 }
 
-__global__ void stft_feat_kernel(const StftParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  float2* data = reinterpret_cast<float2*>(smem_raw);   // [nsig][N]
-  float2* tw = data + p.nsig * p.N;                      // [N/2]
-  __shared__ float s_max[32];
-  const int N = p.N;
-  const int tx = threadIdx.x, sig = threadIdx.y, nthr = blockDim.x;
-  const int b = blockIdx.y, tt = blockIdx.x;
-  const int ns = p.ns_per_utt ? p.ns_per_utt[b] : p.ns;
-  const int frames = 1 + ns / p.hop;                       // librosa center=True frame count
-  const int fr = (p.crop_start[b] + tt) % frames;          // tiling of short utterances (wsj0_2mix.py:118-123)
-  const float* wav = p.wav[sig] + (long long)b * p.ns;
-  float2* d = data + sig * N;
+// One WARP per (frame, signal).  A real N-point frame is transformed as ONE N/2-point complex FFT of
+// z[m] = x[2m] + i x[2m+1] (radix-4 passes = two fused radix-2 stages, in the warp's private shared-memory
+// buffer, __syncwarp between passes) followed by the even/odd split X[k] = E[k] + W_N^k O[k],
+// X[N/2-k] = conj(E[k] - W_N^k O[k]).  A CTA of STFT_WARPS warps holds STFT_WARPS/nsig frames in flight and walks
+// the (utterance, frame) list persistently; the twiddle table exp(-2 pi i k/N), k <= N/2 -- which is also the Hann
+// window, 0.5 - 0.5 Re tw[k] -- is built once per CTA.  Two CTA barriers per batch of frames (spectra complete ->
+// outputs, which for the cos-difference read the mixture's spectrum of the sibling warp).
+constexpr int STFT_WARPS = 12;
 
-  for (int n = tx; n < N; n += nthr) {
-    int pos = fr * p.hop - N / 2 + n;
-    if (pos < 0) pos = -pos;
-    if (pos >= ns) pos = 2 * (ns - 1) - pos;
-    pos = max(0, min(ns - 1, pos));
-    const float v = wav[pos] * hann_periodic(n, N);
-    d[__brev((unsigned)n) >> (32 - p.logN)] = make_float2(v, 0.f);
-  }
-  for (int k = sig * nthr + tx; k < N / 2; k += nthr * blockDim.y) {
+__global__ void __launch_bounds__(STFT_WARPS * 32) stft_feat_kernel(const StftParams p, int items) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int N = p.N, M = N >> 1, logM = p.logN - 1;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);          // [N/2 + 1]
+  float2* zall = tw + (M + 2);                               // [STFT_WARPS][M + 2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slots = STFT_WARPS / p.nsig;
+  const int slot = warp / p.nsig, sig = warp - slot * p.nsig;
+  float2* z = zall + (size_t)warp * (M + 2);
+  const float2* z_mix = zall + (size_t)(slot * p.nsig) * (M + 2);
+  for (int k = tid; k <= M; k += blockDim.x) {
     float sn, cs;
     sincospif(-2.0f * (float)k / (float)N, &sn, &cs);
     tw[k] = make_float2(cs, sn);
   }
   __syncthreads();
-  fft_radix2<false>(d, tw, N, tx, nthr);
-
-  const long long obase = ((long long)b * p.T + tt) * p.F;
-  float lmax = -INFINITY;
-  for (int k = tx; k < p.F; k += nthr) {
-    const float2 X = d[k];
-    const float mg = sqrtf(X.x * X.x + X.y * X.y);
-    if (p.mag[sig]) p.mag[sig][obase + k] = mg;
-    if (p.ph[sig]) {
-      p.ph[sig][(obase + k) * 2] = X.x;
-      p.ph[sig][(obase + k) * 2 + 1] = X.y;
+  for (int base = blockIdx.x * slots; base < items; base += gridDim.x * slots) {
+    const int item = base + slot;
+    const bool active = item < items && slot < slots;
+    int b = 0, tt = 0;
+    if (active) {
+      b = item / p.T;
+      tt = item - b * p.T;
+      const int ns = p.ns_per_utt ? p.ns_per_utt[b] : p.ns;
+      const int frames = 1 + ns / p.hop;                       // librosa center=True frame count
+      const int fr = (p.crop_start[b] + tt) % frames;          // tiling of short utterances (wsj0_2mix.py:118-123)
+      const float* wav = p.wav[sig] + (long long)b * p.ns;
+      const int pos0 = fr * p.hop - M;
+      for (int m = lane; m < M; m += 32) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = 2 * m + e;
+          int pos = pos0 + n;
+          if (pos < 0) pos = -pos;                             // reflect padding (librosa <= 0.9 default)
+          if (pos >= ns) pos = 2 * (ns - 1) - pos;
+          pos = max(0, min(ns - 1, pos));
+          const float hw = 0.5f - 0.5f * tw[n <= M ? n : N - n].x;   // periodic Hann
+          v[e] = __ldg(wav + pos) * hw;
+        }
+        z[__brev((unsigned)m) >> (32 - logM)] = make_float2(v[0], v[1]);
+      }
+      __syncwarp();
+      // decimation in time on bit-reversed input; pass with half-size h and 2h fused (radix 4)
+      int h = 1;
+      for (; h * 4 <= M; h <<= 2) {
+        const int ts1 = N / (2 * h), ts2 = N / (4 * h);       // twiddle strides in the N-point table
+        for (int t = lane; t < M / 4; t += 32) {
+          const int pos = t & (h - 1);
+          const int i0 = ((t - pos) << 2) + pos;
+          const float2 w1 = tw[pos * ts1], w2 = tw[pos * ts2], w3 = tw[(pos + h) * ts2];
+          float2 a = z[i0], bb = z[i0 + h], c = z[i0 + 2 * h], d = z[i0 + 3 * h];
+          float2 q = make_float2(bb.x * w1.x - bb.y * w1.y, bb.x * w1.y + bb.y * w1.x);
+          bb = make_float2(a.x - q.x, a.y - q.y);
+          a = make_float2(a.x + q.x, a.y + q.y);
+          q = make_float2(d.x * w1.x - d.y * w1.y, d.x * w1.y + d.y * w1.x);
+          d = make_float2(c.x - q.x, c.y - q.y);
+          c = make_float2(c.x + q.x, c.y + q.y);
+          q = make_float2(c.x * w2.x - c.y * w2.y, c.x * w2.y + c.y * w2.x);
+          z[i0] = make_float2(a.x + q.x, a.y + q.y);
+          z[i0 + 2 * h] = make_float2(a.x - q.x, a.y - q.y);
+          q = make_float2(d.x * w3.x - d.y * w3.y, d.x * w3.y + d.y * w3.x);
+          z[i0 + h] = make_float2(bb.x + q.x, bb.y + q.y);
+          z[i0 + 3 * h] = make_float2(bb.x - q.x, bb.y - q.y);
+        }
+        __syncwarp();
+      }
+      if (h < M) {                                            // odd log2(M): one radix-2 pass left (h == M/2)
+        const int ts1 = N / (2 * h);
+        for (int t = lane; t < M / 2; t += 32) {
+          const float2 w = tw[t * ts1];
+          const float2 a = z[t], x = z[t + h];
+          const float2 q = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+          z[t] = make_float2(a.x + q.x, a.y + q.y);
+          z[t + h] = make_float2(a.x - q.x, a.y - q.y);
+        }
+        __syncwarp();
+      }
+      // even/odd split, in place: pair (k, M-k) belongs to one lane
+      for (int k = lane; k <= M / 2; k += 32) {
+        const float2 zk = z[k], zm = z[(M - k) & (M - 1)];
+        const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm) / (2i)
+        const float2 w = tw[k];
+        const float2 P = make_float2(O.x * w.x - O.y * w.y, O.x * w.y + O.y * w.x);
+        z[k] = make_float2(E.x + P.x, E.y + P.y);
+        if (2 * k != M) z[M - k] = make_float2(E.x - P.x, -(E.y - P.y));
+      }
     }
-    if (sig == 0) {
-      const float ft = log10f(mg + 1e-7f);
-      if (p.feature) p.feature[obase + k] = ft;
-      lmax = fmaxf(lmax, ft);
-    } else if (p.cosd[sig - 1]) {
-      const float2 X0 = data[k];
-      p.cosd[sig - 1][obase + k] = cosf(atan2f(X0.y, X0.x) - atan2f(X.y, X.x));
-    }
-  }
-  if (p.feat_max != nullptr) {   // block-uniform
-    lmax = warp_max(lmax);
-    const int flat = sig * nthr + tx;
-    if ((flat & 31) == 0) s_max[flat >> 5] = (sig == 0) ? lmax : -INFINITY;
     __syncthreads();
-    if (flat == 0) {
-      float m = -INFINITY;
-      const int nw = (nthr * blockDim.y + 31) >> 5;
-      for (int w = 0; w < nw; ++w) m = fmaxf(m, s_max[w]);
-      atomic_max_float(p.feat_max + b, m);
+    if (active) {
+      const long long obase = ((long long)b * p.T + tt) * p.F;
+      float lmax = -INFINITY;
+      for (int k = lane; k < p.F; k += 32) {
+        const float2 X = z[k];
+        const float mg = sqrtf(X.x * X.x + X.y * X.y);
+        if (p.mag[sig]) p.mag[sig][obase + k] = mg;
+        if (p.ph[sig]) reinterpret_cast<float2*>(p.ph[sig])[obase + k] = X;
+        if (sig == 0) {
+          const float ft = log10f(mg + 1e-7f);
+          if (p.feature) p.feature[obase + k] = ft;
+          lmax = fmaxf(lmax, ft);
+        } else if (p.cosd[sig - 1]) {
+          const float2 X0 = z_mix[k];
+          p.cosd[sig - 1][obase + k] = cosf(atan2f(X0.y, X0.x) - atan2f(X.y, X.x));
+        }
+      }
+      if (p.feat_max != nullptr && sig == 0) {
+        lmax = warp_max(lmax);
+        if (lane == 0) atomic_max_float(p.feat_max + b, lmax);
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -243,10 +305,21 @@ extern "C" int onssen_stft_features(const float* wav_mix, const float* wav_s1, c
   p.feat_max = feat_max;
   cudaStream_t s = (cudaStream_t)stream;
   if (feat_max) fill_kernel<<<(B + 255) / 256, 256, 0, s>>>(feat_max, B, -INFINITY);
-  const int tps = n_fft / 2 < 128 ? n_fft / 2 : 128;
-  const size_t smem = (size_t)(p.nsig * n_fft + n_fft / 2) * sizeof(float2);
-  dim3 grid(T, B), block(tps, p.nsig);
-  stft_feat_kernel<<<grid, block, smem, s>>>(p);
+  const size_t smem = (size_t)(STFT_WARPS + 1) * (n_fft / 2 + 2) * sizeof(float2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(stft_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 13 * (1024 + 2) * 8) !=
+        cudaSuccess)
+      return ONSSEN_ERR_CUDA;
+    attr_set = true;
+  }
+  const int items = B * T, slots = STFT_WARPS / p.nsig;
+  int per_sm = (int)((200u * 1024u) / smem);
+  if (per_sm > 5) per_sm = 5;
+  if (per_sm < 1) per_sm = 1;
+  int grid = (items + slots - 1) / slots;
+  if (grid > num_sms() * per_sm) grid = num_sms() * per_sm;
+  stft_feat_kernel<<<grid, STFT_WARPS * 32, smem, s>>>(p, items);
   return ONSSEN_CHECK_LAUNCH();
 }
 

@@ -92,11 +92,21 @@ class trainer:
             end = time.time()
             if self.verbose and ((i + 1) % self.log_interval == 0 or i + 1 == len_d):
                 avg = float(loss_sum.item()) / n_steps       # the only device->host read of the loop
+                self._check_bptt_saturation()
                 print('epoch %d, %d/%d, training loss: %f, time estimated: %.2f/%.2f seconds' %
                       (epoch, i + 1, len_d, avg, end - init_time, times.avg * len_d), end='\r')
         if self.verbose:
             print("\n")
         return float(loss_sum.item()) / n_steps if n_steps else avg
+
+    def _check_bptt_saturation(self):
+        """surface clamped recurrent gradients of the persistent BPTT kernel (read with the logged loss)"""
+        from .. import _lib
+        n = _lib.bptt_saturation_count(reset=True)
+        if n:
+            print(f"\nWARNING: {n} recurrent-gradient values exceeded the fp16 exchange range in the last "
+                  f"{self.log_interval} steps (exploding gradient); those steps' gradients were clamped")
+        return n
 
     def validate(self, epoch):
         self.model = self.model.eval()

@@ -17,7 +17,9 @@ _, whh_p, _ = _lib.lstm_pack_layer(wf, wr, H, 2 * H, True, H)
 gates = torch.randn(T * B, 8 * Hp, device="cuda")
 y_h = torch.empty(T * B, 2 * Hp, device="cuda", dtype=torch.float16)
 ws = _lib.blstm_rec_workspace(B, H, "cuda")
-trace = torch.zeros(64 + 32 * 8, device="cuda", dtype=torch.int64)
+trace = torch.zeros(640, device="cuda", dtype=torch.int64)
+if os.environ.get("POLL_DELAY"):
+    lib.onssen_blstm_rec_set_poll_delay(int(os.environ["POLL_DELAY"]))
 for tc in (True,):
     lib.onssen_blstm_rec_set_trace(ctypes.c_void_p(trace.data_ptr()))
     _lib.blstm_rec_fwd(gates, whh_p, B, T, H, y_h, None, 0.3, 1, 0, ws, tc)
@@ -29,7 +31,7 @@ for tc in (True,):
     t0 = gt[:, 0].min()
     print('group trace step 102 (ns rel. to first mma-done): rb: mma_done, publish, gathered')
     for rb in range(19):
-        print(f'   rb{rb:2d}: {gt[rb,0]-t0:6d} {gt[rb,1]-t0:6d} {gt[rb,2]-t0:6d}')
+        print(f'   rb{rb:2d}: {gt[rb,0]-t0:6d} {gt[rb,1]-t0:6d} {gt[rb,2]-t0:6d}   sm {gt[rb,3]}')
     print(f'   publish spread {gt[:,1].max()-gt[:,1].min()} ns; last publish -> first gathered {gt[:,2].min()-gt[:,1].max()} ns; last gathered {gt[:,2].max()-gt[:,1].max()} ns')
     names = {3: "mma warp: h tile ready (bar3)", 4: "mma warp: issued+commit", 8: "gate: mma done", 9: "gate: tmem loaded",
              10: "gate: act+xchg written", 11: "gate: c/h + LL publish", 12: "gate: h gathered", 13: "gate: fenced+arrived"}
@@ -39,6 +41,15 @@ for tc in (True,):
         for slot in sorted(names, key=lambda q: tr[s][q]):
             print(f"   {names[slot]:32s} {tr[s][slot] - base:8d}")
         print(f"   step period: {tr[s][3] - tr[s-1][3]}")
+    wt = full[320:320 + 4 * 64].reshape(4, 64)
+    if wt.any():
+        for s in range(1, 3):
+            base = wt[s][8 * 6 + 0]          # MMA warp: first producer group ready
+            print(f"--- per-warp trace step {100 + s} (cycles rel. to the MMA warp's first-ready); gate warps: mma-done, "
+                  f"published, gather complete, signalled (after fence); MMA warp: first ready, last ready, committed")
+            for w in range(8):
+                print(f"   warp {w}: " + " ".join(f"{int(wt[s][w * 6 + k] - base):7d}" for k in range(4)))
+            print("   mma   : " + " ".join(f"{int(wt[s][8 * 6 + k] - base):7d}" for k in range(3)))
     for _ in range(3):
         _lib.blstm_rec_fwd(gates, whh_p, B, T, H, y_h, None, 0.3, 1, 0, ws, tc)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -63,3 +63,24 @@ def test_phase_net_vs_repaired_oracle(cuda_device):
     want = O.loss_phase([o.cpu().numpy() for o in out], lab_np)
     assert got.shape == (B, B)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=5e-5)
+
+
+def test_l2norm_pairs_backward_matches_autograd(cuda_device):
+    """(ph + x_phase) / |ph + x_phase| over (re, im) pairs (phase_network.py:55-56,63-66): the hand-written backward
+    against torch autograd of F.normalize on the same fp32 inputs, at the cfg4 bin count; elementwise, so tight."""
+    import torch.nn.functional as Fn
+    from onssen_b200 import _lib
+    B, T, F = 4, 50, 257
+    g = torch.Generator(device="cpu").manual_seed(3)
+    ph = torch.randn(B, T, F, 2, generator=g).to(cuda_device)
+    xp = torch.randn(B, T, F, 2, generator=g).to(cuda_device)
+    dy = torch.randn(B, T, F, 2, generator=g).to(cuda_device)
+    v = (ph.clone().requires_grad_(True))
+    out = Fn.normalize(v + xp, p=2, dim=-1)
+    out.backward(dy)
+    dz, sc = _lib.l2norm_pairs_bwd(dy, ph, xp)                     # time-major [T*B][2F]
+    want = v.grad.permute(1, 0, 2, 3).reshape(T * B, 2 * F)
+    scale = want.abs().max().item()
+    assert (dz - want).abs().max().item() < 1e-5 * scale
+    assert torch.allclose(_lib.add_l2norm_pairs(ph, xp), out.detach(), atol=1e-6)
+    assert abs(sc[0].item() * sc[1].item() - 1.0) < 1e-6 and 256 <= scale * sc[0].item() <= 2048   # power-of-two scale

@@ -43,9 +43,13 @@ def compare(ours, ref, loss_ours, loss_ref, inp, lab, out_tols, loss_rtol, grad_
     torch.set_num_threads(os.cpu_count() or 8)
     ref.load_state_dict({k: v.detach().cpu() for k, v in ours.state_dict().items()})
     ours.train(); ref.train()
+    from onssen_b200 import _lib
+    _lib.bptt_saturation_count(reset=True)
     out = ours(inp)
     lo = loss_ours(out, lab)
     torch.mean(lo).backward()
+    nsat = _lib.bptt_saturation_count(reset=True)
+    print(f"{tag} BPTT exchange values clamped: {nsat}")
     out_r = ref([t.cpu() for t in inp])
     lr = loss_ref(out_r, [t.cpu() for t in lab])
     torch.mean(lr).backward()
@@ -61,20 +65,19 @@ def compare(ours, ref, loss_ours, loss_ref, inp, lab, out_tols, loss_rtol, grad_
     lrel = float((lo.detach().cpu() - lr.detach()).abs().max() / lr.detach().abs().max())
     print(f"{tag} loss rel dev {lrel:.3e} (limit {loss_rtol:g})")
     assert lrel < loss_rtol
-    worst = ("", 0.0)
     ref_grads = dict(ref.named_parameters())
+    errs = []
     for k, p in ours.named_parameters():
         assert p.grad is not None, k
-        e = rel_err(p.grad.cpu(), ref_grads[k].grad)
-        if e > worst[1]:
-            worst = (k, e)
-        assert e < grad_rtol, (k, e)
-    print(f"{tag} worst relative gradient error {worst[1]:.3e} ({worst[0]})")
+        errs.append((rel_err(p.grad.cpu(), ref_grads[k].grad), k))
+    errs.sort(reverse=True)
+    print(f"{tag} worst relative gradient errors: " + ", ".join(f"{k} {e:.3e}" for e, k in errs[:4]))
+    assert errs[0][0] < grad_rtol, errs[:4]
     # running statistics of train-mode BatchNorm follow the reference (momentum 0.1, unbiased variance)
     for k, v in ours.state_dict().items():
         if "running_" in k:
             torch.testing.assert_close(v.cpu(), ref.state_dict()[k], rtol=2e-3, atol=2e-4)
-    return lrel, worst[1]
+    return lrel, errs[0][0]
 
 
 def test_cfg2_deep_clustering_b32_vs_reference(cuda_device):
@@ -123,9 +126,35 @@ def test_cfg4_phase_net_f257_vs_repaired_restatement(cuda_device):
     F, H, L, D, B = 257, 300, 3, 20, 16
     ours = ob.nn.phase_net(F, H, L, D, dropout=0.0).to(cuda_device)
     ref = PhaseNetRepaired(F, H, L, D)
+    # A freshly initialised mask head gives mask_A ~ mask_B ~ 0.5, which makes the two PIT assignments of the mask loss
+    # tie to ~1e-5 relative: the arg-min (and with it the whole phase-loss gradient) is then decided by rounding.  The
+    # loss is continuous there but its gradient is not, so the comparison is made at a point where the permutation is
+    # well separated: speaker-0 mask biased up, speaker-1 mask biased down (output index f*2 + s, chimera.py:42-45).
+    with torch.no_grad():
+        b = ours.chimera.fc_mi.bias.view(F, 2)
+        b[:, 0] += 1.0
+        b[:, 1] -= 1.0
+        # The (re, im) normalisation v/|v| with v = fc_phase(y) + x_phase has a 1/|v| gradient.  With a default-size
+        # fc_phase output (|ph| ~ 0.3) a few of the 1.6 M bins land within 1e-3 of ph = -x_phase; their 1/|v| ~ 1e3
+        # contributions dominate the whole gradient and flip with a 1e-4 change of ph (measured: the SAME kernels give
+        # 4e-2 at T=40 and 1.0 at T=400 relative error against fp32 torch, while d loss / d phase matches to 5e-4) --
+        # the repaired model is ill-conditioned there, in any arithmetic.  A small phase head keeps |v| ~ |x_phase|,
+        # where mag_mix / |v| is bounded, so the comparison checks the kernels rather than the conditioning.
+        ours.fc_phase.weight.mul_(0.01)
+        ours.fc_phase.bias.mul_(0.01)
     inp, lab = synth_inputs("phase", B, 512, 128, 64000, 400, cuda_device, first=300)
     # gradients: the (re,im) normalisation divides by |v|, tiny on quiet bins -> looser limit
     # phase outputs are v/|v|: an absolute error e on v moves the unit vector by ~e/|v| -> weight by min(1, |v|)
     wts = lambda r: [None, None, None] + [n.clamp(max=1.0)[..., None] for n in r.pre_norms]
     compare(ours, ref, ob.loss.loss_phase, loss_phase_repaired, inp, lab, out_tols=[2e-3, 1e-3, 1e-3, 3e-3, 3e-3],
             loss_rtol=2e-4, grad_rtol=3e-2, tag="cfg4", weights=wts)
+    # the permutation margin of the reference at this point (relative gap of the two PIT sums per utterance)
+    with torch.no_grad():
+        _, m_a, m_b, _, _ = ref([t.cpu() for t in inp])
+        mix, s1, s2 = (t.cpu() for t in lab[1:4])
+        l1n = lambda x: x.abs().reshape(B, -1).sum(1)
+        lm1 = l1n(m_a * mix - s1) + l1n(m_b * mix - s2)
+        lm2 = l1n(m_b * mix - s1) + l1n(m_a * mix - s2)
+        margin = ((lm1 - lm2).abs() / torch.minimum(lm1, lm2)).min().item()
+    print(f"cfg4 smallest relative PIT margin {margin:.3e}")
+    assert margin > 1e-3
