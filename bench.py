@@ -15,6 +15,7 @@ Extra keys of the GPU arm's JSON line (beyond the driver contract):
   gpu_reference  the UNMODIFIED reference modules (oracle/_ref) `.to('cuda')` -- cuDNN LSTM / cuBLAS / ATen -- on the
                  same device, same tensors, same warm-up / steps / CUDA events: the same-B200 bar (N=1 only)
   configs        fwd+loss and train-step ms of BASELINE configs[2..4] (cfg3 at B=64; the per-GPU shards of cfg4 / cfg5)
+  e2e_disk       training throughput fed from wav files on disk through the data plugin (wall clock, N=1)
   ddp_check      (N>1) parameter-checksum spread across ranks after the train steps, and the N-rank averaged
                  gradient against the 1-rank gradient of the concatenated batch
 """
@@ -351,6 +352,54 @@ def time_gpu_reference(torch, dev, ob, dev_batches, K, W):
     return out
 
 
+def time_disk_training(torch, ob, dev, model, opt, K):
+    """Training steps fed FROM DISK through the data plugin: a temporary wsj0-2mix-layout corpus of
+    synthetic 16-bit wavs (4 batches x 32 utterances x {mix,s1,s2}), `wsj0_2mix_dataloader` (thread-pool PCM staging two
+    batches ahead, decode + featurizer on the device), forward + loss + backward + clip + Adam; WALL CLOCK per step
+    over whole epochs, first epoch untimed."""
+    import shutil
+    import tempfile
+    from scipy.io import wavfile
+    B, nb = CFG["B"], 4
+    root = tempfile.mkdtemp(prefix="onssen_b200_bench_")
+    try:
+        from oracle import onssen_oracle as O
+        for sub in ("mix", "s1", "s2"):
+            os.makedirs(os.path.join(root, "wav8k", "min", "tr", sub))
+        q = lambda x: np.clip(np.round(x * 32768), -32768, 32767).astype(np.int16)
+        for i in range(B * nb):
+            for sub, x in zip(("mix", "s1", "s2"), O.synth_utterance(7000 + i, CFG["nsample"])):
+                wavfile.write(os.path.join(root, "wav8k", "min", "tr", sub, f"u{i:04d}.wav"), 8000, q(x))
+        fo = dict(data_path=root, batch_size=B, frame_length=T_FRAMES, sampling_rate=8000, window_size=CFG["n_fft"],
+                  hop_size=CFG["hop"], db_threshold=DB)
+        loader = ob.data.wsj0_2mix_dataloader("dc", fo, "tr", dev)
+
+        def epoch():
+            n = 0
+            for inp, lab in loader:
+                loss = torch.mean(ob.loss.loss_dc(model(inp), lab))
+                opt.zero_grad()
+                loss.backward()
+                ob.utils.clip_grad_norm_(model.parameters(), 5)
+                opt.step()
+                n += 1
+            return n
+
+        epoch()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        steps = 0
+        while steps < K:
+            steps += epoch()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": B * steps / dt, "unit": "utterances/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
+                "files_per_step": 3 * B, "timing": "wall clock (host decode threads + device), one GPU",
+                "loader": "wsj0_2mix_dataloader: 8 decode threads, 2 batches staged ahead, int16 -> float + STFT on device"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def ddp_check(torch, ob, dev, rank, world, model_after_training):
     """(i) spread of a parameter checksum across ranks after the timed train steps; (ii) relative error of the
     world-averaged gradient (SyncBN + global loss coupling on) against the 1-rank gradient of the concatenated batch,
@@ -492,6 +541,12 @@ def run_gpu(args):
         ms_train = torch.tensor([g0.elapsed_time(g1)], device=dev)
         train_loss = float(tl.item())
     clocks = sampler.stop() if rank == 0 else None
+    disk = None
+    if world == 1 and not args.no_train and not args.no_disk:
+        try:
+            disk = time_disk_training(torch, ob, dev, model, opt, KT)
+        except Exception as exc:
+            disk = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
@@ -561,6 +616,10 @@ def run_gpu(args):
                              "includes": "featurizer + forward + loss_dc + hand-written backward (BPTT) + "
                                          "bucketed NCCL gradient all-reduce (N>1) + clip_grad_norm_(5) + Adam "
                                          "(multi-tensor kernels of this repo)"}
+        if disk is not None:
+            line["e2e_disk"] = disk
+            if "ms_per_step" in disk and ms_train is not None:
+                disk["fraction_of_device_resident_train"] = (ms_train.item() / KT) / disk["ms_per_step"]
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
             if "fwd_loss_ms" in gpu_ref:
@@ -585,6 +644,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step figure")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 block")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the same-GPU reference (cuDNN) leg")
+    ap.add_argument("--no-disk", action="store_true", help="skip the from-disk training figure (e2e_disk)")
     ap.add_argument("--sync-bn", action="store_true",
                     help="training figure with whole-batch BatchNorm statistics across ranks (N>1)")
     args = ap.parse_args()

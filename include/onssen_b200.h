@@ -367,6 +367,17 @@ size_t onssen_kmeans_scratch_bytes(void);
 int onssen_kmeans_masks(const float* emb, const float* feature, long long N, int D, int K, float db_threshold,
                         int iters, float* masks, int32_t* labels, void* scratch, void* stream);
 
+/* ---- wav decode on the device (onssen/data/feature_utils.py:15-19) -----------------------------
+ * pcm_i16 [R][pitch*channels] interleaved int16, frames[r] valid frames of row r -> out [R][pitch] float32 mono
+ * (sample / 32768, mean over channels: what librosa.load(sr=None) returns), zero beyond frames[r]. */
+int onssen_pcm16_to_f32(const void* pcm_i16, int R, int pitch, int channels, const int32_t* frames, float* out,
+                        void* stream);
+/* Polyphase resampling y = upfirdn(h, x, up, down)[n_pre_remove : n_pre_remove + ceil(n_in*up/down)] per row, i.e.
+ * scipy.signal.resample_poly with the filter h (designed on the host, data/wavio.py:resample_filter); stands in for
+ * librosa.core.resample (feature_utils.py:19).  x [R][pitch_in], y [R][pitch_out] (zero beyond the row's length). */
+int onssen_resample_poly(const float* x, int R, int pitch_in, const int32_t* n_in, int up, int down, const float* h,
+                         int hlen, int n_pre_remove, float* y, int pitch_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

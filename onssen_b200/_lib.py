@@ -35,6 +35,8 @@ _SIGNATURES = {
     "onssen_blstm_rec_workspace_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_set_trace": (None, [c_vp]),
     "onssen_blstm_rec_set_poll_delay": (None, [c_int]),
+    "onssen_pcm16_to_f32": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "onssen_resample_poly": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_blstm_rec_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_f, c_ull, c_ull, c_vp, c_sz,
                                      c_int, c_vp]),
     "onssen_bn_num_chunks": (c_int, [c_int]),
@@ -781,3 +783,26 @@ def kmeans_masks(emb, feature, K=2, db_threshold=40.0, iters=30, want_labels=Fal
                                  N, D, K, float(db_threshold), int(iters), _p(masks), _p(labels), _p(scratch), _stream())
     _check(rc, "onssen_kmeans_masks")
     return (masks, labels) if want_labels else masks
+
+
+def pcm16_to_f32(pcm, channels, frames):
+    """pcm int16 (R, pitch*channels) CUDA, frames int32 (R,) CUDA -> float32 (R, pitch) mono (sample/32768)"""
+    lib = load()
+    R = pcm.shape[0]
+    pitch = pcm.shape[1] // channels
+    out = torch.empty(R, pitch, device=pcm.device, dtype=torch.float32)
+    _check(lib.onssen_pcm16_to_f32(_p(_req(pcm, torch.int16, "pcm")), R, pitch, int(channels),
+                                   _p(_req(frames, torch.int32, "frames")), _p(out), _stream()), "onssen_pcm16_to_f32")
+    return out
+
+
+def resample_poly(x, n_in, max_n_in, up, down, h, n_pre_remove):
+    """x float32 (R, pitch_in) CUDA, n_in int32 (R,) CUDA; h float32 filter on the device -> (y (R, pitch_out), pitch_out)"""
+    lib = load()
+    R, pitch_in = x.shape
+    pitch_out = (int(max_n_in) * up + down - 1) // down
+    y = torch.empty(R, pitch_out, device=x.device, dtype=torch.float32)
+    _check(lib.onssen_resample_poly(_p(_req(x, torch.float32)), R, pitch_in, _p(_req(n_in, torch.int32)), int(up),
+                                    int(down), _p(_req(h, torch.float32)), h.numel(), int(n_pre_remove), _p(y), pitch_out,
+                                    _stream()), "onssen_resample_poly")
+    return y, pitch_out

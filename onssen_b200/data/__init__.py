@@ -2,8 +2,8 @@
 from .feature_utils import featurize_batch, num_crop_starts
 from .daps_enhance import daps_enhance_dataloader
 from .edinburgh_tts import edinburgh_tts_dataloader
-from .prefetch import DevicePrefetcher
+from . import wavio
 from .wsj0_2mix import wsj0_2mix_dataloader
 
 __all__ = ["featurize_batch", "num_crop_starts", "wsj0_2mix_dataloader", "edinburgh_tts_dataloader",
-           "daps_enhance_dataloader", "DevicePrefetcher"]
+           "daps_enhance_dataloader", "wavio"]

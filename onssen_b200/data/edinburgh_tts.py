@@ -10,7 +10,7 @@ import random
 import numpy as np
 import torch
 
-from . import feature_utils
+from . import feature_utils, wavio
 from .wsj0_2mix import _opt, _read_wav
 
 
@@ -44,13 +44,26 @@ class _EdinburghLoader:
             if self.device.type == "cuda" else torch.from_numpy
         return [to(b) for b in bufs], torch.from_numpy(lengths)
 
+    def _waveform_batches(self, batches):
+        """-> ((mix, clean, noise) device waveforms, lengths) per batch; on CUDA the raw PCM is staged by a thread pool
+        ahead of the consumer and decoded / resampled on the device (data/wavio.py)"""
+        if self.device.type != "cuda":
+            for names in batches:
+                yield self._load(names)
+            return
+        pairs = [[(fn, fn.replace("/noisy_trainset_28spk_wav", "/clean_trainset_28spk_wav")) for fn in names]
+                 for names in batches]
+        sr = _opt(self.fo, "sampling_rate")
+        for staged in wavio.PcmStager(pairs):
+            (mix, clean), lengths = wavio.device_waveforms(staged, sr, self.device)
+            yield (mix, clean, mix - clean), lengths          # noise as "speaker 2" (get_stft_from_subtraction)
+
     def __iter__(self):
         order = list(range(len(self.file_list)))
         random.shuffle(order)
         fo = self.fo
-        for i in range(0, len(order), self.batch_size):
-            names = [self.file_list[j] for j in order[i:i + self.batch_size]]
-            (mix, s1, s2), lengths = self._load(names)
+        batches = [[self.file_list[j] for j in order[i:i + self.batch_size]] for i in range(0, len(order), self.batch_size)]
+        for names, ((mix, s1, s2), lengths) in zip(batches, self._waveform_batches(batches)):
             inp, lab = feature_utils.featurize_batch(mix, s1, s2, "dc" if self.model_name == "dc" else self.model_name,
                                                      _opt(fo, "window_size"), _opt(fo, "hop_size"),
                                                      _opt(fo, "frame_length"), _opt(fo, "db_threshold"),

@@ -18,7 +18,7 @@ import random
 import numpy as np
 import torch
 
-from . import feature_utils
+from . import feature_utils, wavio
 
 
 def _read_wav(fn, sampling_rate):
@@ -77,6 +77,10 @@ class _WavBatchLoader:
         full_path = _opt(feature_options, "data_path") + "/wav8k/min/" + partition + "/mix/*.wav"
         files = sorted(glob.glob(full_path))
         self.file_list = shard_files(files, rank, world_size, batch_size)
+        opt = lambda k, d: (feature_options.get(k, d) if isinstance(feature_options, dict)
+                            else getattr(feature_options, k, d))
+        self.workers = int(opt("num_workers", 8))       # decode threads (extra keys; the reference has no workers)
+        self.prefetch = int(opt("prefetch_batches", 2))  # batches staged ahead of the training step
 
     def __len__(self):
         return (len(self.file_list) + self.batch_size - 1) // self.batch_size
@@ -100,9 +104,18 @@ class _WavBatchLoader:
         order = list(range(len(self.file_list)))
         if self.shuffle:
             random.shuffle(order)
-        for i in range(0, len(order), self.batch_size):
-            names = [self.file_list[j] for j in order[i:i + self.batch_size]]
-            (mix, s1, s2), lengths = self._load(names)
+        batches = [[self.file_list[j] for j in order[i:i + self.batch_size]] for i in range(0, len(order), self.batch_size)]
+        if self.device.type != "cuda":
+            for names in batches:                      # host decode (the featurizer itself needs a CUDA device)
+                (mix, s1, s2), lengths = self._load(names)
+                yield self._featurize(mix, s1, s2, lengths)
+            return
+        # CUDA: raw PCM is staged by a thread pool `prefetch` batches ahead (data/wavio.py); int16 -> float, channel
+        # mean and (if the rate differs) resampling run on the device; nothing is decoded on this thread
+        triples = [[(fn, fn.replace("/mix", "/s1"), fn.replace("/mix", "/s2")) for fn in names] for names in batches]
+        sr = _opt(self.fo, "sampling_rate")
+        for staged in wavio.PcmStager(triples, workers=self.workers, depth=self.prefetch):
+            (mix, s1, s2), lengths = wavio.device_waveforms(staged, sr, self.device)
             yield self._featurize(mix, s1, s2, lengths)
 
     def _featurize(self, mix, s1, s2, lengths):

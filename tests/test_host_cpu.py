@@ -201,3 +201,47 @@ def test_batch_si_sdr_matches_reference_fixture():
     est = ref[:, [2, 0, 1]] + 0.1 * torch.from_numpy(rng.standard_normal((2, 3, 500)))
     sdr3, p3 = batch_si_sdr(est, ref, return_perm=True)
     assert sdr3.dtype == torch.float64 and (sdr3 > 15).all() and (p3 == p3[0]).all()
+
+
+def test_wavio_headers_and_resample_filter(tmp_path):
+    """data/wavio.py on the host: RIFF walking for the sample formats the loaders accept, the raw-PCM staging of a batch,
+    and the polyphase filter bookkeeping -- evaluating y[j] = sum_i x[i] h[(j + pre) down - i up] (the formula the CUDA
+    kernel implements) must reproduce scipy.signal.resample_poly."""
+    import numpy as np
+    from scipy.io import wavfile
+    from scipy.signal import resample_poly
+    from onssen_b200.data import wavio
+    rng = np.random.RandomState(0)
+    a16 = (rng.standard_normal(1000) * 5000).astype(np.int16)
+    st16 = (rng.standard_normal((700, 2)) * 5000).astype(np.int16)
+    a32 = (rng.standard_normal(500) * 1e8).astype(np.int32)
+    f32 = rng.standard_normal(300).astype(np.float32)
+    for name, rate, arr in (("a.wav", 8000, a16), ("b.wav", 16000, st16), ("c.wav", 44100, a32), ("d.wav", 8000, f32)):
+        wavfile.write(str(tmp_path / name), rate, arr)
+        r, ch, code, got = wavio.read_pcm(str(tmp_path / name))
+        assert r == rate and ch == (arr.shape[1] if arr.ndim > 1 else 1) and got.dtype == arr.dtype
+        np.testing.assert_array_equal(got.reshape(arr.shape), arr)
+    assert np.allclose(wavio.to_float_mono(st16, "i2"), (st16.astype(np.float32) / 32768).mean(1))
+    # staging: (a, a) and (short, a) pairs -> one int16 block, per-utterance length = the shorter file
+    wavfile.write(str(tmp_path / "e.wav"), 8000, a16[:600])
+    names = [[(str(tmp_path / "a.wav"), str(tmp_path / "a.wav")), (str(tmp_path / "e.wav"), str(tmp_path / "a.wav"))]]
+    item = next(iter(wavio.PcmStager(names, workers=2, depth=1)))
+    assert item["pcm"].shape == (2, 2, 1000) and item["lengths"].tolist() == [1000, 600] and item["rate"] == 8000
+    assert torch.equal(item["pcm"][1, 1, :600], torch.from_numpy(a16[:600])) and int(item["pcm"][0, 1, 600:].abs().max()) == 0
+    with pytest.raises(ValueError, match="differ in sampling rate"):
+        next(iter(wavio.PcmStager([[(str(tmp_path / "a.wav"), str(tmp_path / "b.wav"))]], workers=1)))
+    # polyphase bookkeeping vs scipy for three rate pairs
+    x = rng.standard_normal(997).astype(np.float32)
+    for rin, rout in ((16000, 8000), (44100, 16000), (8000, 16000)):
+        up, down, h, pre = wavio.resample_filter(rin, rout)
+        want = resample_poly(x.astype(np.float64), up, down)
+        n_out = -(-len(x) * up // down)
+        assert len(want) == n_out
+        y = np.zeros(n_out)
+        for j in range(n_out):
+            t = (j + pre) * down
+            i_hi = min(len(x) - 1, t // up)
+            i_lo = max(0, -(-(t - len(h) + 1) // up))
+            idx = np.arange(i_lo, i_hi + 1)
+            y[j] = np.dot(x[idx].astype(np.float64), h[t - idx * up].astype(np.float64))
+        assert np.abs(y - want).max() < 1e-6 * np.abs(want).max(), (rin, rout)

@@ -83,22 +83,52 @@ def test_trainer_validate_and_tester_eval(cuda_device, tmp_path):
     assert (rec[0, 0] - mix).abs().max().item() < 2e-4 * mix.abs().max().item() + 1e-4   # s1+s2 == mix up to int16 rounding
 
 
-def test_device_prefetcher_matches_inline_featurizer(cuda_device):
+def test_loader_decodes_and_resamples_on_the_device(cuda_device, tmp_path):
+    """16 kHz stereo int16 files with feature_options.sampling_rate = 8000: raw PCM staged by the thread pool, int16 ->
+    float mono and the polyphase resampling on the device; waveforms must equal scipy.signal.resample_poly of the host
+    decode (feature_utils.py:15-19 behaviour with the documented filter), features the oracle's of those waveforms."""
+    from scipy.io import wavfile
+    from scipy.signal import resample_poly
     import onssen_b200 as ob
-    B, T = 2, 50
-    batches = []
-    for k in range(3):
-        utts = [O.synth_utterance(10 * k + i, 6000) for i in range(B)]
-        ws = [torch.from_numpy(np.stack([u[j] for u in utts])).pin_memory() for j in range(3)]
-        batches.append((ws[0], ws[1], ws[2], torch.tensor([k, 2 * k], dtype=torch.int32)))
-    got = list(ob.data.DevicePrefetcher(batches, "chimera++", 256, 64, T, 40, cuda_device))
-    assert len(got) == 3
-    for (inp, lab), item in zip(got, batches):
-        ri, rl = ob.data.featurize_batch(*[t.to(cuda_device) for t in item[:3]], "chimera++", 256, 64, T, 40,
-                                         crop_start=item[3])
-        torch.cuda.synchronize()
-        for a, b in zip(inp + lab, ri + rl):
-            assert torch.equal(a, b)
+    from onssen_b200.data import wavio
+    for sub in ("mix", "s1", "s2"):
+        os.makedirs(tmp_path / "wav8k" / "min" / "tr" / sub, exist_ok=True)
+    rng = np.random.RandomState(5)
+    host = []
+    for i in range(3):
+        n = 20000 + 1234 * i
+        sig = {}
+        for sub in ("mix", "s1", "s2"):
+            x = (rng.standard_normal((n, 2)) * 3000).astype(np.int16)
+            t = np.arange(n) / 16000.0
+            x[:, 0] += (8000 * np.sin(2 * np.pi * (300 + 100 * i) * t)).astype(np.int16)
+            wavfile.write(str(tmp_path / "wav8k" / "min" / "tr" / sub / f"u{i}.wav"), 16000, x)
+            mono = (x.astype(np.float32) / 32768.0).mean(axis=1)
+            sig[sub] = resample_poly(mono, 1, 2).astype(np.float32)
+        host.append(sig)
+    names = [[tuple(str(tmp_path / "wav8k" / "min" / "tr" / sub / f"u{i}.wav") for sub in ("mix", "s1", "s2"))
+              for i in range(3)]]
+    staged = next(iter(wavio.PcmStager(names, workers=4, depth=1)))
+    assert staged["pcm"].dtype == torch.int16 and staged["pcm"].is_pinned() and staged["channels"] == 2
+    (mix, s1, s2), lengths = wavio.device_waveforms(staged, 8000, cuda_device)
+    assert lengths.tolist() == [len(h["mix"]) for h in host]
+    for b, h in enumerate(host):
+        for dev, key in ((mix, "mix"), (s1, "s1"), (s2, "s2")):
+            got = dev[b, :lengths[b]].cpu().numpy()
+            assert np.abs(got - h[key]).max() < 2e-6 * np.abs(h[key]).max() + 1e-7
+            assert float(dev[b, lengths[b]:].abs().max() if dev.shape[1] > lengths[b] else 0.0) == 0.0
+    # and through the loader factory (same files): features of the resampled waveforms
+    fo = dict(data_path=str(tmp_path), batch_size=3, frame_length=60, sampling_rate=8000, window_size=256, hop_size=64,
+              db_threshold=40, num_workers=3, prefetch_batches=1)
+    loader = ob.data.wsj0_2mix_dataloader("dc", fo, "tr", cuda_device)
+    loader.shuffle = False
+    np.random.seed(3)
+    inp, lab = next(iter(loader))
+    np.random.seed(3)
+    for b, h in enumerate(host):
+        start = np.random.randint(O.num_crop_starts(len(h["mix"]), 64, 60))
+        ri, rl = O.featurize(h["mix"], h["s1"], h["s2"], 256, 64, 60, start, 40, "dc")
+        np.testing.assert_allclose(lab[1][b].cpu().numpy(), rl[1], atol=1e-5 * rl[1].max())
 
 
 def test_daps_loader_segments_match_oracle(cuda_device, tmp_path):
