@@ -233,6 +233,9 @@ int onssen_unpack_lstm_grad(const float* gp, int H, int K, int in_is_blstm, int 
  * order [dir][unit block][k-step][m-tile][lane][4 words] (permuted gate rows, zero padded) so that every operand
  * load of the BPTT step kernel is one coalesced 16-byte access. */
 int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, int H, void* out, void* stream);
+/* fp16 elements of `out` above: the fragment layout is followed by the same matrix as the tcgen05 BPTT kernel's
+ * tensor-memory slabs [dir][unit block of 128][K quarter][128 units][Hp gate rows]. */
+size_t onssen_lstm_pack_whh_t_elems(int H);
 /* Forward recurrence that also saves the BPTT state: the activated gates overwrite gates_inout in place, c_out
  * [T*B][2Hp] fp32, h_raw [T*B][2Hp] fp16 = h before dropout (NULL when dropout_p == 0: use y_h). */
 int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
@@ -243,10 +246,12 @@ int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int
  * (the dropout mask is re-derived from seed/offset); scratch: onssen_blstm_rec_bwd_scratch_bytes(B, H) (cell
  * gradient carry + the per-step dG exchange buffer in B-fragment order), zeroed by the call. */
 size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H);
-/* 1 (default): one persistent cooperative launch per layer (W_hh^T resident in smem, flag-bit dG exchange; requires
- * the scale passed to onssen_blstm_rec_bwd to keep |dG*scale| < 2, i.e. scale2 from a target <= 2^-4 * headroom);
+/* 2 (default): persistent tcgen05 kernel -- W_hh^T resident in tensor memory, K split over 4-CTA clusters, partial dh
+ * reduce-scattered through distributed shared memory (falls back to 1 when the shape does not fit one launch);
+ * 1: persistent mma.sync kernel (W_hh^T resident in smem). Both exchange dG with a flag bit inside the fp16 data and
+ * require the scale passed to onssen_blstm_rec_bwd to keep |dG*scale| < 2 (scale2 from a target <= 2^-4 * headroom);
  * 0: one launch per time step (validation path). */
-void onssen_blstm_rec_bwd_set_persistent(int on);
+void onssen_blstm_rec_bwd_set_persistent(int mode);
 /* debug: clock64 stamps of CTA 0 of the persistent BPTT kernel, steps 100..107, [step][slot 0..7][warp 0..7]
    (512 int64); NULL = off */
 void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64);

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "onssen_unpack_linear_grad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "onssen_unpack_lstm_grad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "onssen_lstm_pack_whh_t": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
+    "onssen_lstm_pack_whh_t_elems": (c_sz, [c_int]),
     "onssen_blstm_rec_fwd_train": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_ull, c_ull,
                                            c_vp, c_sz, c_vp]),
     "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
@@ -568,7 +569,7 @@ def unpack_lstm_grad(gp, H, K, in_is_blstm, Hin, direction, Kp=None):
 def lstm_pack_whh_t(w_hh_f, w_hh_r, H):
     lib = load()
     Hp = hp_of(H)
-    out = torch.empty(2, Hp, 4 * Hp, device=w_hh_f.device, dtype=torch.float16)
+    out = torch.empty(lib.onssen_lstm_pack_whh_t_elems(H), device=w_hh_f.device, dtype=torch.float16)
     _check(lib.onssen_lstm_pack_whh_t(_p(_req(w_hh_f.detach(), torch.float32)), _p(_req(w_hh_r.detach(), torch.float32)),
                                       H, _p(out), _stream()), "onssen_lstm_pack_whh_t")
     return out

@@ -8,25 +8,10 @@
 // dG (fp32, in place over the saved activations, and as scaled fp16 for the next launch / the wgrad GEMMs).
 // dh_rec and the cell-gradient carry never leave the CTA's unit block.  L2-bound: 2 x 4Hp x (32+B) fp16 per CTA.
 #include "common.cuh"
+#include "lstm_bwd.cuh"
 
 namespace onssen {
 namespace {
-
-struct BwdParams {
-  float* actg;          // [T*B][2*4Hp] activated gates (i,f,g,o) -> overwritten with dG (fp32)
-  __half* dg16;         // [T*B][2*4Hp] scaled fp16 dG
-  const float* c;       // [T*B][2*Hp]
-  const float* dy;      // [T*B][2*Hp] gradient w.r.t. the layer output (after dropout)
-  const uint32_t* wt;   // W_hh^T in mma A-fragment order: [dir][ub][kstep][mtile][lane][4 words]
-  uint32_t* frag;       // dG of the last processed step in B-fragment order: [parity][dir][bb][kstep][ntile][lane][2]
-  float* dc;            // [2][B][Hp] cell-gradient carry
-  const float* scale2;  // {scale, 1/scale}
-  unsigned int* sat;    // optional: number of published values that had to be clamped into the flag range (or NaN)
-  int B, T, H, Hp, s;
-  float dropout_p;
-  unsigned int seed_lo, seed_hi;
-  long long* trace;     // debug: clock64 stamps of CTA (0,0,0), steps [BWD_TRACE_S0, +8): [step][slot 0..7][warp 0..7]
-};
 
 long long* g_bwd_trace = nullptr;
 #define BWD_TRACE_S0 100
@@ -46,7 +31,7 @@ __device__ __forceinline__ float hash_uniform32(unsigned int seed_lo, unsigned i
   return (float)(x >> 8) * (1.0f / 16777216.0f);
 }
 
-int g_bwd_persistent = 1;   // 0: one launch per step (validation path), see onssen_blstm_rec_bwd_set_persistent
+int g_bwd_persistent = 2;   // 2: tcgen05 cluster kernel, 1: mma.sync persistent kernel, 0: one launch per step (validation)
 
 __device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, const uint32_t* b) {
   asm volatile(
@@ -541,10 +526,40 @@ __global__ void pack_whh_t_kernel(const float* __restrict__ w_f, const float* __
   }
 }
 
+// W_hh [4H][H] fp32 (both directions) -> the tcgen05 BPTT kernel's TMEM slabs (fp16):
+// [dir][unit block of 128][K quarter kq][unit row r][k]: gate row n = kq*Hp + k (n = 4*unit' + gate), hidden unit
+// u = 128*ub + r; zero outside [0,H).  One row = the Hp/2 TMEM words of one lane.
+__global__ void pack_whh_slab_kernel(const float* __restrict__ w_f, const float* __restrict__ w_r, int H, int Hp,
+                                     __half* __restrict__ out) {
+  const int nub = bwd_tc_nub(Hp);
+  const long long total = 2LL * nub * 4 * 128 * Hp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long tt = idx;
+    const int k = (int)(tt % Hp); tt /= Hp;
+    const int r = (int)(tt & 127); tt >>= 7;
+    const int kq = (int)(tt & 3); tt >>= 2;
+    const int ub = (int)(tt % nub);
+    const int dir = (int)(tt / nub);
+    const int n = kq * Hp + k;
+    const int ur = n >> 2, gate = n & 3;
+    const int u = ub * 128 + r;
+    float v = 0.f;
+    if (ur < H && u < H) v = (dir ? w_r : w_f)[(long long)(gate * H + ur) * H + u];
+    out[idx] = to_half_sat(v);
+  }
+}
+
 }  // namespace
 }  // namespace onssen
 
 using namespace onssen;
+
+extern "C" size_t onssen_lstm_pack_whh_t_elems(int H) {
+  if (H <= 0) return 0;
+  const int Hp = hp_of(H);
+  return whh_t_frag_elems(Hp) + whh_t_slab_elems(Hp);
+}
 
 extern "C" int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, int H, void* out, void* stream) {
   if (!w_hh_f || !w_hh_r || !out || H <= 0) return ONSSEN_ERR_ARG;
@@ -552,16 +567,24 @@ extern "C" int onssen_lstm_pack_whh_t(const float* w_hh_f, const float* w_hh_r, 
   long long g = (2LL * Hp * 4 * Hp + 255) / 256;
   if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
   pack_whh_t_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w_hh_f, w_hh_r, H, Hp, (__half*)out);
+  pack_whh_slab_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w_hh_f, w_hh_r, H, Hp,
+                                                                 (__half*)out + whh_t_frag_elems(Hp));
   return ONSSEN_CHECK_LAUNCH();
 }
 
-extern "C" void onssen_blstm_rec_bwd_set_persistent(int on) { g_bwd_persistent = on ? 1 : 0; }
-extern "C" void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64) { g_bwd_trace = (long long*)device_buf_512_int64; }
+extern "C" void onssen_blstm_rec_bwd_set_persistent(int mode) { g_bwd_persistent = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+extern "C" void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64) {
+  g_bwd_trace = (long long*)device_buf_512_int64;
+  bwd_tc_set_trace((long long*)device_buf_512_int64);
+}
+
+static size_t bwd_frag_bytes(int B, int Hp) { return (size_t)2 * 2 * ((B + 31) / 32) * (4 * Hp / 16) * 4 * 32 * 2 * 4; }
 
 extern "C" size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H) {
   const int Hp = hp_of(H);
   // dc carry [2][B][Hp] fp32 + fragment exchange [2 parity][2 dir][nbb][4Hp/16][4][32][2] u32
-  return (size_t)2 * B * Hp * 4 + (size_t)2 * 2 * ((B + 31) / 32) * (4 * Hp / 16) * 4 * 32 * 2 * 4;
+  // (+ the tcgen05 kernel's exchange tiles; only one of the two exchange areas is used by a given launch)
+  return (size_t)2 * B * Hp * 4 + bwd_frag_bytes(B, Hp) + bwd_tc_xbuf_bytes(B, Hp);
 }
 
 extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c, const float* dy, const void* whh_t,
@@ -574,6 +597,8 @@ extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c
   BwdParams p;
   p.actg = act_gates; p.dg16 = (__half*)dg16; p.c = c; p.dy = dy; p.wt = (const uint32_t*)whh_t; p.dc = dc_carry;
   p.frag = (uint32_t*)((uint8_t*)scratch + (size_t)2 * B * hp_of(H) * 4);
+  p.xbuf = (uint8_t*)p.frag + bwd_frag_bytes(B, hp_of(H));
+  p.wslab = (const __half*)whh_t + whh_t_frag_elems(hp_of(H));
   p.scale2 = scale2; p.sat = (unsigned int*)sat_count_u32; p.B = B; p.T = T; p.H = H; p.Hp = hp_of(H);
   p.dropout_p = dropout_p;
   const unsigned long long mix = seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
@@ -582,7 +607,12 @@ extern "C" int onssen_blstm_rec_bwd(float* act_gates, void* dg16, const float* c
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(scratch, 0, onssen_blstm_rec_bwd_scratch_bytes(B, H), s) != cudaSuccess) return ONSSEN_ERR_CUDA;
   p.trace = g_bwd_trace;
-  // persistent path: W_hh^T fragments resident in smem, one cooperative launch for all T steps
+  // tcgen05 path: W_hh^T resident in tensor memory, K split over 4-CTA clusters (lstm_bwd_tc.cu)
+  if (g_bwd_persistent == 2) {
+    const int rc = launch_bwd_tc(p, s);
+    if (rc != ONSSEN_ERR_UNSUPPORTED) return rc;
+  }
+  // mma.sync persistent path: W_hh^T fragments resident in smem, one cooperative launch for all T steps
   if (g_bwd_persistent) {
     for (int nt = 2; nt <= 4; nt += 2) {
       const int nb = 8 * nt;

@@ -18,7 +18,7 @@ else
 fi
 $NVCC $FLAGS $DEFS -c $IN -o $C/build/var_$NAME/$base.o
 objs=""
-for f in capi gemm_tc05 lstm_rec lstm_bwd pack loss stft extras backward optim kmeans wav; do
+for f in capi gemm_tc05 lstm_rec lstm_bwd lstm_bwd_tc pack loss stft extras backward optim kmeans wav; do
   if [ $f == $base ]; then objs="$objs $C/build/var_$NAME/$base.o"; else objs="$objs $C/build/$f.o"; fi
 done
 $NVCC -shared -o $ROOT/onssen_b200/libonssen_b200_$NAME.so $objs -lcudart

@@ -21,15 +21,25 @@ dg16 = torch.empty(M, 8 * Hp, device="cuda", dtype=torch.float16)
 trace = torch.zeros(512, device="cuda", dtype=torch.int64)
 names = {0: "step start", 1: "dG fragments fresh (warp 0)", 2: "MMAs done, partials in smem", 3: "after barrier",
          4: "gate math + publish issued", 5: "MMAs done (all chunks)", 6: "publish issued"}
-for persistent in (1,):
+MODE = int(os.environ.get("MODE", 2))
+tc_names = {0: "step start", 1: "dG quarter gathered", 2: "fenced + arrived", 3: "mma warp: tile ready", 4: "mma warp: issued + commit",
+            5: "mma done", 6: "partials sent (DSMEM)", 7: "4 partials received", 8: "dG published", 9: "dG stored"}
+for persistent in (MODE,):
     lib.onssen_blstm_rec_bwd_set_persistent(persistent)
     act = act0.clone()
     lib.onssen_blstm_rec_bwd_set_trace(ctypes.c_void_p(trace.data_ptr()))
     _lib.blstm_rec_bwd(act, dg16, c, dy, whh_t, sc, B, T, H, 0.3, 1, 0)
     torch.cuda.synchronize()
     lib.onssen_blstm_rec_bwd_set_trace(None)
+    if persistent == 2:
+        tr = trace.cpu().numpy()[:64].reshape(4, 16)
+        for s in range(1, 4):
+            t0 = tr[s][0]
+            print(f"--- step {100 + s}: period {t0 - tr[s - 1][0]} cycles (thread 0 step start = 0)")
+            for slot in sorted(tc_names, key=lambda q: tr[s][q]):
+                print(f"   {tc_names[slot]:32s} {tr[s][slot] - t0:7d}")
     tr = trace.cpu().numpy().reshape(8, 8, 8)          # [step][slot][warp]
-    for s in range(1, 3):
+    for s in range(1, 3) if persistent != 2 else ():
         t0 = tr[s][0][0]
         print(f"--- step {100 + s}: period {t0 - tr[s - 1][0][0]} cycles (warp 0 step start = 0)")
         for slot in (0, 1, 5, 2, 3, 6, 4):
