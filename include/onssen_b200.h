@@ -252,6 +252,10 @@ size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H);
  * require the scale passed to onssen_blstm_rec_bwd to keep |dG*scale| < 2 (scale2 from a target <= 2^-4 * headroom);
  * 0: one launch per time step (validation path). */
 void onssen_blstm_rec_bwd_set_persistent(int mode);
+/* SMs the tcgen05 BPTT kernel leaves free (default 0). Its CTAs must all be co-resident (cooperative launch, one CTA
+ * per SM); a data-parallel trainer overlaps the gradient all-reduce of the layer above with this kernel and sets the
+ * reserve to what the collective's kernel occupies, so that neither launch has to wait for the other to drain. */
+void onssen_blstm_rec_bwd_set_sm_reserve(int sms);
 /* debug: clock64 stamps of CTA 0 of the persistent BPTT kernel, steps 100..107, [step][slot 0..7][warp 0..7]
    (512 int64); NULL = off */
 void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64);

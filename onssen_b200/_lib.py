@@ -68,6 +68,7 @@ _SIGNATURES = {
     "onssen_blstm_rec_bwd_scratch_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_bwd_set_persistent": (None, [c_int]),
     "onssen_blstm_rec_bwd_set_trace": (None, [c_vp]),
+    "onssen_blstm_rec_bwd_set_sm_reserve": (None, [c_int]),
     "onssen_clip_grad_norm": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "onssen_adam_step": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_ll, c_vp]),
     "onssen_kmeans_scratch_bytes": (c_sz, []),
@@ -128,6 +129,8 @@ def load():
         fn = getattr(lib, name)      # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("ONSSEN_BPTT_MODE"):   # 2 (default) tcgen05 cluster kernel, 1 mma.sync persistent, 0 per step
+        lib.onssen_blstm_rec_bwd_set_persistent(int(os.environ["ONSSEN_BPTT_MODE"]))
     _lib = lib
     return lib
 

@@ -578,6 +578,8 @@ extern "C" void onssen_blstm_rec_bwd_set_trace(void* device_buf_512_int64) {
   bwd_tc_set_trace((long long*)device_buf_512_int64);
 }
 
+extern "C" void onssen_blstm_rec_bwd_set_sm_reserve(int sms) { bwd_tc_set_sm_reserve(sms); }
+
 static size_t bwd_frag_bytes(int B, int Hp) { return (size_t)2 * 2 * ((B + 31) / 32) * (4 * Hp / 16) * 4 * 32 * 2 * 4; }
 
 extern "C" size_t onssen_blstm_rec_bwd_scratch_bytes(int B, int H) {

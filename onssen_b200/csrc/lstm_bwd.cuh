@@ -35,5 +35,6 @@ size_t bwd_tc_xbuf_bytes(int B, int Hp);
 // (the caller falls back to the mma.sync kernels).
 int launch_bwd_tc(const BwdParams& p, cudaStream_t stream);
 void bwd_tc_set_trace(long long* buf);
+void bwd_tc_set_sm_reserve(int sms);
 
 }  // namespace onssen

@@ -37,6 +37,7 @@ constexpr int BT_TRACE_S0 = 100;
 constexpr size_t BT_MIN_SMEM = 120 * 1024;          // > half of an SM's shared memory: one CTA per SM (512 TMEM columns each)
 
 long long* g_tc_trace = nullptr;
+int g_tc_sm_reserve = 0;   // SMs left free for concurrent kernels (NCCL all-reduce of the layer above), see bwd_tc_set_sm_reserve
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -483,6 +484,7 @@ int launch_tc(const BwdParams& p, int S, int Bs, cudaStream_t stream) {
 }  // namespace
 
 void bwd_tc_set_trace(long long* buf) { g_tc_trace = buf; }
+void bwd_tc_set_sm_reserve(int sms) { g_tc_sm_reserve = sms < 0 ? 0 : sms; }
 
 namespace {
 struct TcPlan { int nbp, S, Bs; };
@@ -498,7 +500,9 @@ bool plan_tc(int B, int Hp, TcPlan& pl) {
     maxc_hp = Hp;
   }
   for (int nbp = 16; nbp <= 32; nbp += 16) {
-    const int maxc = nbp == 16 ? maxc16 : maxc32;
+    int maxc = nbp == 16 ? maxc16 : maxc32;
+    const int avail = (num_sms() - g_tc_sm_reserve) / 4;
+    if (maxc > avail) maxc = avail;
     const int smax = maxc / (2 * nub);
     if (smax < 1 || (B + nbp - 1) / nbp > smax) continue;
     int S = smax < B ? smax : B;

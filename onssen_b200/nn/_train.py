@@ -83,6 +83,12 @@ def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None, 
         dg16 = torch.empty(M, 8 * Hp, device=dev, dtype=torch.float16)
         whh_t = _lib.lstm_pack_whh_t(wf[1], wr[1], H)
         _lib.blstm_rec_bwd(lay["gates"], dg16, lay["c"], dY, whh_t, sc, B, T, H, lay["p"], lay["seed"], l)
+        if l == 0 and on_grads is not None:
+            # the last cooperative launch of the backward is enqueued: gradient buckets held back so far (GradSync
+            # without overlap) can be all-reduced beside the weight-gradient GEMMs that follow
+            flush = getattr(getattr(on_grads, "__self__", None), "flush", None)
+            if flush is not None:
+                flush()
         dG32 = lay["gates"]                      # now the fp32 pre-activation gradients
         inv = sc[1:]
         gb = _lib.colsum(dG32)                   # [8Hp], permuted

@@ -1,7 +1,7 @@
 """Gradient synchronisation for one-process-per-GPU data parallel training (the reference has none; SURVEY.md
 section 8e): bucketed all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests) launched as soon as a
-group of gradients is final -- head/BN first, then each BLSTM layer top-down -- so the collective overlaps the
-remaining BPTT launches; results are averaged over ranks.
+group of gradients is final -- head/BN first, then each BLSTM layer top-down -- (overlap mode) or as one grouped
+launch after the backward (the NCCL default, see GradSync); results are averaged over ranks.
 
     sync = GradSync()                 # after dist.init_process_group
     model.grad_sync = sync            # DCFunction.backward feeds it bucket by bucket
@@ -12,34 +12,66 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, group=None):
+    def __init__(self, group=None, overlap=None):
+        """overlap: launch each bucket's all-reduce as soon as it is final (beside the remaining BPTT launches) instead
+        of one grouped all-reduce after the backward.  Default: off for NCCL.  Measured on 2 x B200 at cfg2
+        (scripts/ddp_train_steps.py): the persistent recurrence kernels are cooperative launches that need 114-120 free
+        SMs, so an all-reduce kernel that is resident when one of them is launched (or the reverse) makes one wait for
+        the other to drain, and each rank's NCCL kernel spins on its peer meanwhile: overlapped 12.85 ms/step vs 11.77
+        on one GPU, while the whole 108 MB all-reduce costs ~0.3 ms when it runs alone.  ONSSEN_DDP_OVERLAP=1 turns the
+        overlap back on (it pays when the collective is slow: gloo, PCIe)."""
+        import os
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.pending = []
+        self.deferred = []
         self.bytes_reduced = 0
         self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        if overlap is None:
+            overlap = (not self.nccl) or os.environ.get("ONSSEN_DDP_OVERLAP", "0") == "1"
+        self.overlap = bool(overlap)
+        if self.nccl and self.world > 1 and self.overlap:
+            # leave the collective's share of the SMs free (two batch slices instead of three in the BPTT kernel)
+            from .. import _lib
+            _lib.load().onssen_blstm_rec_bwd_set_sm_reserve(int(os.environ.get("ONSSEN_DDP_SM_RESERVE", "48")))
+
+    def _launch_nccl(self, tensors):
+        # ONE grouped launch of in-place AVG all-reduces (ncclGroupStart/End through torch's coalescing manager): no
+        # flatten copy, no copy-back, no divide pass
+        with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        return cm
 
     def reduce_bucket(self, grads):
-        """grads: dict name -> tensor (final).  NCCL: ONE grouped launch of in-place AVG all-reduces over the bucket's
-        tensors (ncclGroupStart/End through torch's coalescing manager): no flatten copy, no copy-back, no divide pass.
-        Other backends (gloo in the CPU tests): flatten, SUM, and write the average back in wait()."""
+        """grads: dict name -> tensor (final).  NCCL: grouped in-place AVG all-reduces, launched now (overlap) or all
+        together in wait().  Other backends (gloo in the CPU tests): flatten, SUM, and write the average back in
+        wait()."""
         if self.world == 1 or not grads:
             return
         names = sorted(grads)
         tensors = [grads[n] for n in names]
         self.bytes_reduced += sum(t.numel() * t.element_size() for t in tensors)
         if self.nccl:
-            with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
-                for t in tensors:
-                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
-            self.pending.append((cm, None, names, grads))
+            if self.overlap:
+                self.pending.append((self._launch_nccl(tensors), None, names, grads))
+            else:
+                self.deferred.extend(tensors)
             return
         flat = torch.cat([t.reshape(-1) for t in tensors])
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.pending.append((work, flat, names, grads))
 
+    def flush(self):
+        """Launch the all-reduce of the buckets held back so far (called by the backward once its last cooperative
+        kernel is enqueued: the collective then runs beside the remaining weight-gradient GEMMs)."""
+        if self.deferred:
+            self.pending.append((self._launch_nccl(self.deferred), None, None, None))
+            self.deferred = []
+
     def wait(self):
         """Blocks (the stream, for NCCL) until every bucket is reduced; afterwards the tensors hold the rank average."""
+        self.flush()
         for work, flat, names, grads in self.pending:
             work.wait()
             if flat is None:

@@ -22,6 +22,8 @@ trace = torch.zeros(512, device="cuda", dtype=torch.int64)
 names = {0: "step start", 1: "dG fragments fresh (warp 0)", 2: "MMAs done, partials in smem", 3: "after barrier",
          4: "gate math + publish issued", 5: "MMAs done (all chunks)", 6: "publish issued"}
 MODE = int(os.environ.get("MODE", 2))
+if os.environ.get("RESERVE") is not None:
+    lib.onssen_blstm_rec_bwd_set_sm_reserve(int(os.environ["RESERVE"]))
 tc_names = {0: "step start", 1: "dG quarter gathered", 2: "fenced + arrived", 3: "mma warp: tile ready", 4: "mma warp: issued + commit",
             5: "mma done", 6: "partials sent (DSMEM)", 7: "4 partials received", 8: "dG published", 9: "dG stored"}
 for persistent in (MODE,):
