@@ -30,8 +30,12 @@ namespace {
 
 using namespace tc05;
 
-constexpr int REC_GATE_WARPS = 8;
-constexpr int REC_THREADS = (REC_GATE_WARPS + 1) * 32;  // 8 gate warps + 1 control warp
+// Gate warps of the tensor-core path: thread = one gate row x 8 batch columns, so a slice of NB = 16 / 24 / 32 columns
+// takes 8 / 12 / 16 warps (4 warps cover the 128 TMEM lanes).  (Round 1 ran 32-column slices on 8 warps, 16 columns per
+// thread: 43 KB of SASS, more than the 32 KB instruction cache the step body streams through once per step.)
+// The SIMT validation path keeps 8 warps.
+__host__ __device__ constexpr int rec_gate_warps(int nb, bool tc) { return tc ? nb / 2 : 8; }
+__host__ __device__ constexpr int rec_threads(int nb, bool tc) { return (rec_gate_warps(nb, tc) + 1) * 32; }  // + MMA warp
 constexpr int TMEM_A_COL = 128;                         // first TMEM column of the resident W_hh slice
 constexpr int NACC = 2;   // independent accumulators (columns a*NBP): back-to-back MMAs into ONE accumulator
                           // serialise on the ~70-cycle accumulate latency when N is this small
@@ -129,9 +133,11 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
 // CHUNK: the launch covers a column chunk of a larger batch (row pitch p.Bp > p.B, absolute dropout indices); the
 // whole-batch instantiation keeps the round-1 register allocation (two more live parameters spill at NB = 32).
 template <int NB, bool TC, bool CHUNK>
-__global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecParams p) {
+__global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const RecParams p) {
+  constexpr int REC_GATE_WARPS = rec_gate_warps(NB, TC);
+  constexpr int REC_THREADS = rec_threads(NB, TC);
   constexpr int NBP = NB <= 16 ? 16 : 32;  // MMA N / rows of the h operand tile
-  constexpr int NBH = NB / 2;              // batch columns per gate-warp half
+  constexpr int NBH = NB / (REC_GATE_WARPS / 4);   // batch columns per gate warp (4 warps cover the 128 TMEM lanes)
   constexpr int XP = NB + 1;               // exchange tile pitch (floats)
   constexpr int GT = REC_GATE_WARPS * 32;  // gate threads
   extern __shared__ __align__(128) uint8_t smem[];
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
   } else {
     // ===================== gate warps =====================
     const int q = warp & 3;         // TMEM lane quarter
-    const int half = warp >> 2;     // which half of the batch columns this warp owns
+    const int half = warp >> 2;     // which group of NBH batch columns this warp owns
     const int r = q * 32 + lane;    // gate row inside the row block: r = 4*ul + gate
     const int gate = r & 3;
     const int ul = r >> 2;          // unit inside the row block (0..31)
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) blstm_rec_kernel(const RecPara
     // gather: 16-byte chunks (kc, n) = 8 consecutive units of one column; chunk c = kc*NBP + n at byte 16*c
     // in both the global exchange tile and the smem operand tile.  Thread handles c = tid + GT*i.
     const int nchunks = Hp * NBP / 8;
-    constexpr int MAXCH = NBP == 16 ? 6 : 12;
+    constexpr int MAXCH = (768 * NBP / 8 + GT - 1) / GT;   // Hp <= 768
     const int my_chunks = (nchunks - tid + GT - 1) / GT;   // <= MAXCH (checked on the host)
     unsigned int want_mask = 0;                            // chunks of real batch columns only (pads stay 0)
     for (int i = 0; i < my_chunks; ++i)
@@ -488,6 +494,7 @@ size_t rec_smem_bytes(int Hp) {
 template <int NB, bool TC>
 int launch_rec(RecParams& p, int grid, cudaStream_t stream) {
   const size_t smem = rec_smem_bytes<NB, TC>(p.Hp);
+  constexpr int REC_THREADS = rec_threads(NB, TC);
   auto kern = (p.Bp != p.B) ? blstm_rec_kernel<NB, TC, true> : blstm_rec_kernel<NB, TC, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return ONSSEN_ERR_CUDA;
@@ -507,6 +514,7 @@ template <bool TC>
 int dispatch_nb(int nb, RecParams& p, int grid, cudaStream_t stream) {
   switch (nb) {
     case 16: return launch_rec<16, TC>(p, grid, stream);
+    case 24: if constexpr (TC) return launch_rec<24, TC>(p, grid, stream); else return launch_rec<32, TC>(p, grid, stream);
     case 32: return launch_rec<32, TC>(p, grid, stream);
     default: return ONSSEN_ERR_UNSUPPORTED;
   }
@@ -527,7 +535,7 @@ SlicePlan plan_slices(int B, int H) {
   if (smax < 1 || Hp / 2 + TMEM_A_COL > 512 || Hp > 768) { sp.ok = false; return sp; }
   if (smax > B) smax = B;
   int bs = (B + smax - 1) / smax;
-  static const int opts[] = {16, 32};   // NB == NBP: all operand-tile columns are published every step
+  static const int opts[] = {16, 24, 32};
   int nb = -1;
   for (int o : opts) if (o >= bs) { nb = o; break; }
   if (nb < 0) { sp.ok = false; return sp; }
