@@ -198,6 +198,12 @@ int onssen_loss_pit_l1_fwd(const float* mask_a, const float* mask_b, long long m
  */
 /* onssen_gemm_f16 with two extras: out_scale (device scalar multiplied into the accumulators, NULL = 1) and, for
  * epi 3, inv_norm [output rows][N/group] = 1/max(||z||, 1e-12) of every normalised group (NULL to skip). */
+/* Weight-gradient GEMM (the dW = dZ^T A products autograd forms behind onssen/utils/train.py:82):
+ * out[m][n] = out_scale * sum_k X[k][m] * Y[k + y_row_shift][n], X [Kc][ldx], Y [Kc][ldy] fp16 row-major, contracted
+ * over their ROWS and read in place (MN-major tcgen05 operands, no transposed copies); rows of Y outside [0, Kc) count
+ * as zero (y_row_shift = -B / +B pairs dG_t with h_{t-1} of the forward / reverse direction); out fp32 [M][ld_out]. */
+int onssen_gemm_f16_rows(const void* X, const void* Y, float* out, int M, int N, int Kc, long long ldx, long long ldy,
+                         long long ld_out, int y_row_shift, const float* out_scale, void* stream);
 int onssen_gemm_f16_ex(const void* A, const void* W, const float* bias, float* out, int M, int N, int K,
                        long long lda, long long ldw, long long ld_out, int epi, int group, int remap_inner,
                        int remap_outer, const float* out_scale, float* inv_norm, void* stream);

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "onssen_pack_linear_f16": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_gemm_l2norm_supported": (c_int, [c_int]),
     "onssen_gemm_f16": (c_int, [c_vp] * 4 + [c_int] * 3 + [c_ll] * 3 + [c_int] * 4 + [c_vp]),
+    "onssen_gemm_f16_rows": (c_int, [c_vp] * 3 + [c_int] * 3 + [c_ll] * 3 + [c_int] + [c_vp] * 2),
     "onssen_blstm_rec_workspace_bytes": (c_sz, [c_int, c_int]),
     "onssen_blstm_rec_set_trace": (None, [c_vp]),
     "onssen_blstm_rec_set_poll_delay": (None, [c_int]),
@@ -469,6 +470,18 @@ def gemm_f16_ex(A, W, bias, out, M, N, K, ld_out, epi=0, group=0, remap_inner=0,
     rc = lib.onssen_gemm_f16_ex(_p(_req(A, torch.float16)), _p(_req(W, torch.float16)), _p(bias), _p(out), M, N, K,
                                 A.stride(0), W.stride(0), ld_out, epi, group, remap_inner, remap_outer,
                                 _p(out_scale), _p(inv_norm), _stream())
+    _check(rc, "onssen_gemm_f16")
+    return out
+
+
+def gemm_f16_rows(X, Y, out, M, N, Kc, y_row_shift=0, out_scale=None):
+    """out[m][n] = out_scale * sum_k X[k][m] * Y[k + y_row_shift][n] (X, Y fp16 row-major views, out fp32 [M][N])."""
+    lib = load()
+    for t in (X, Y):     # row-major views (column slices of a wider buffer are fine)
+        if not t.is_cuda or t.dtype != torch.float16 or t.dim() != 2 or t.stride(1) != 1:
+            raise OnssenB200Error("gemm_f16_rows operands must be 2-D fp16 CUDA tensors with unit column stride")
+    rc = lib.onssen_gemm_f16_rows(_p(X), _p(Y), _p(out), M, N, Kc, X.stride(0), Y.stride(0), out.stride(0), int(y_row_shift),
+                                  _p(out_scale), _stream())
     _check(rc, "onssen_gemm_f16")
     return out
 

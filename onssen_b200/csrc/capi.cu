@@ -39,6 +39,13 @@ extern "C" int onssen_gemm_f16(const void* A, const void* W, const float* bias, 
                           (cudaStream_t)stream);
 }
 
+extern "C" int onssen_gemm_f16_rows(const void* X, const void* Y, float* out, int M, int N, int Kc, long long ldx,
+                                    long long ldy, long long ld_out, int y_row_shift, const float* out_scale,
+                                    void* stream) {
+  if (!X || !Y || !out) return ONSSEN_ERR_ARG;
+  return onssen::gemm_f16_rows(X, Y, out, M, N, Kc, ldx, ldy, ld_out, y_row_shift, out_scale, (cudaStream_t)stream);
+}
+
 extern "C" int onssen_gemm_f16_ex(const void* A, const void* W, const float* bias, float* out, int M, int N,
                                   int K, long long lda, long long ldw, long long ld_out, int epi, int group,
                                   int remap_inner, int remap_outer, const float* out_scale, float* inv_norm,

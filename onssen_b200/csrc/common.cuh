@@ -14,6 +14,8 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
              long long ldw, long long ld_out, int epi, int group, int remap_inner, int remap_outer,
              cudaStream_t stream, const float* out_scale = nullptr, float* inv_norm = nullptr);
 bool gemm_l2norm_group_supported(int group);
+int gemm_f16_rows(const void* X, const void* Y, float* out, int M, int N, int Kc, long long ldx, long long ldy,
+                  long long ld_out, int y_row_shift, const float* out_scale, cudaStream_t stream);
 
 inline int hp_of(int H) { return ((H + 31) / 32) * 32; }
 

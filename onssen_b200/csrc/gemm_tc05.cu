@@ -43,6 +43,10 @@ struct GemmParams {
   int num_m_blocks, num_n_blocks;
   const float* out_scale;  // optional device scalar: accumulators are multiplied by *out_scale (before bias)
   float* inv_norm;         // optional (epi 3): 1/max(||z||,eps) per (output row, group) -> [rows][N/group]
+  // "rows" mode (weight gradients): both operands are stored [k][m] / [k][n] (the contraction runs over their ROWS),
+  // read in place as MN-major UMMA operands: TMA boxes of 64 k-rows x 64 columns (128 B, 128B swizzle), 8 KB each.
+  int mn_major;
+  int b_row_shift;         // rows mode: B row k + b_row_shift pairs with A row k (time shift of the W_hh gradient)
 };
 
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
@@ -122,6 +126,18 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int n_blk = tile / p.num_m_blocks;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.mn_major) {
+            const int nbox_b = (BN + 63) / 64;
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 + nbox_b) * 8192u);
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d(smem_a + stage * A_STAGE_BYTES + j * 8192, &tmap_a, &full_bar[stage], m_blk * BM + 64 * j,
+                          kb * BK);
+            for (int j = 0; j < nbox_b; ++j)   // rows outside [0, K) (time shift) and columns >= N are zero-filled
+              tma_load_2d(smem_b + stage * B_STAGE_BYTES + j * 8192, &tmap_w, &full_bar[stage], n_blk * BN + 64 * j,
+                          kb * BK + p.b_row_shift);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
           tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &full_bar[stage], kb * BK, n_blk * BN);
@@ -132,7 +148,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BM, BN);
+      // rows mode: a_major = b_major = MN (instruction-descriptor bits 15 / 16)
+      const uint32_t idesc = make_idesc_f16(BM, BN) | (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -147,11 +164,22 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          if (p.mn_major) {
+            // MN-major, 128B swizzle: 64 columns x 8 k-rows per 1 KB atom; LBO = next 64-column box (8 KB),
+            // SBO = next 8 k-rows (1 KB); one MMA (K = 16) spans two atoms
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 2048, 8192, 1024, 2);
+              const uint64_t db = make_smem_desc(b_addr + k * 2048, 8192, 1024, 2);
+              umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+              umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -326,6 +354,20 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rows, int K, long long
   return r == CUDA_SUCCESS ? ONSSEN_OK : ONSSEN_ERR_DRIVER;
 }
 
+// rows mode: source [rows = contraction][cols] fp16 row-major; dims {cols, rows}, box {64 columns, 64 rows}
+int make_tmap_f16_rows(CUtensorMap* map, const void* base, int rows, int cols, long long ld_elems) {
+  auto fn = get_encode_fn();
+  if (fn == nullptr) return ONSSEN_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ONSSEN_OK : ONSSEN_ERR_DRIVER;
+}
+
 int pick_block_n(int N, int epi, int group) {
   if (epi == 3) {
     // largest multiple of lcm(group,16) that is <= 256
@@ -372,6 +414,7 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ld_out = ld_out; p.epi = epi; p.group = group;
   p.remap_inner = remap_inner; p.remap_outer = remap_outer; p.block_n = bn;
   p.out_scale = out_scale; p.inv_norm = inv_norm;
+  p.mn_major = 0; p.b_row_shift = 0;
   p.num_m_blocks = (M + BM - 1) / BM;
   p.num_n_blocks = (N + bn - 1) / bn;
   CUtensorMap ta, tw;
@@ -392,6 +435,29 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
       default: return ONSSEN_ERR_UNSUPPORTED;
     }
   }
+  return launch<0>(ta, tw, p, stream);
+}
+
+// out[m][n] = out_scale * sum_k X[k][m] * Y[k + y_row_shift][n]   (rows of Y outside [0, Kc) count as zero)
+// X: [Kc][ldx] fp16, Y: [Kc][ldy] fp16, both row-major and read in place (MN-major UMMA operands): the weight
+// gradients dW = dZ^T A contract over the T*B rows of two time-major buffers, no transposed copies.
+int gemm_f16_rows(const void* X, const void* Y, float* out, int M, int N, int Kc, long long ldx, long long ldy,
+                  long long ld_out, int y_row_shift, const float* out_scale, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || Kc <= 0) return ONSSEN_ERR_ARG;
+  if ((ldx & 7) || (ldy & 7) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Y) & 15))
+    return ONSSEN_ERR_ARG;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = Kc; p.bias = nullptr; p.out = out; p.ld_out = ld_out; p.epi = 0; p.group = 0;
+  p.remap_inner = 0; p.remap_outer = 0; p.block_n = pick_block_n(N, 0, 0);
+  p.out_scale = out_scale; p.inv_norm = nullptr;
+  p.mn_major = 1; p.b_row_shift = y_row_shift;
+  p.num_m_blocks = (M + BM - 1) / BM;
+  p.num_n_blocks = (N + p.block_n - 1) / p.block_n;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_f16_rows(&ta, X, Kc, M, ldx);
+  if (rc != ONSSEN_OK) return rc;
+  rc = make_tmap_f16_rows(&tw, Y, Kc, N, ldy);
+  if (rc != ONSSEN_OK) return rc;
   return launch<0>(ta, tw, p, stream);
 }
 

@@ -51,11 +51,11 @@ def linear_backward(dz32, sc, a_in_h, w_p, N, H, grads, name, K=None, want_dA=Tr
     plain K-feature input padded to Kp.  Fills grads[name.weight/bias]; returns dA [M][Kp] (or None)."""
     M = dz32.shape[0]
     Kp, Mp = a_in_h.shape[1], _lib.pad64(M)
-    dz_n, dz_t = _lib.cast_transpose_f16(dz32, sc, want_n=want_dA)
+    # dW = dz^T a contracts over the M rows of two row-major buffers: read in place (MN-major tcgen05 operands)
+    dz_n, _ = _lib.cast_transpose_f16(dz32, sc, want_n=True, want_t=False)
     grads[name + ".bias"] = _lib.colsum(dz32)
-    aT = _lib.transpose_shift_f16(a_in_h, 0, Kp)
     dWp = torch.empty(N, Kp, device=dz32.device, dtype=torch.float32)
-    _lib.gemm_f16_ex(dz_t, aT, None, dWp, N, Kp, Mp, Kp, out_scale=sc[1:])
+    _lib.gemm_f16_rows(dz_n[:, :N], a_in_h, dWp, N, Kp, M, out_scale=sc[1:])
     grads[name + ".weight"] = (_lib.unpack_linear_grad(dWp, N, 2 * H, True, H) if K is None
                                else _lib.unpack_linear_grad(dWp, N, K, False, 0))
     if not want_dA:
@@ -94,18 +94,19 @@ def blstm_backward(rnn, layers, packed, dY, B, T, grads, prefix, on_grads=None, 
         gb = _lib.colsum(dG32)                   # [8Hp], permuted
         kp_in = lay["a_in"].shape[1]
         I_l = rnn.input_size if l == 0 else 2 * H
-        dgT = _lib.transpose_shift_f16(dg16, 0, 8 * Hp)
-        xT = _lib.transpose_shift_f16(lay["a_in"], 0, kp_in)
+        # weight gradients contract over the M = T*B rows of dG and of the layer's input / hidden state: both are read
+        # in place as MN-major tcgen05 operands (round 1 made transposed fp16 copies: 6 % of the training step)
         dWih_p = torch.empty(8 * Hp, kp_in, device=dev, dtype=torch.float32)
-        _lib.gemm_f16_ex(dgT, xT, None, dWih_p, 8 * Hp, kp_in, Mp, kp_in, out_scale=inv)
+        _lib.gemm_f16_rows(dg16, lay["a_in"], dWih_p, 8 * Hp, kp_in, M, out_scale=inv)
         for d, suf in enumerate(("", "_reverse")):
             grads[f"{prefix}weight_ih_l{l}{suf}"] = _lib.unpack_lstm_grad(dWih_p, H, I_l, l > 0, H if l > 0 else 0, d)
             gbd = _lib.unpack_lstm_grad(gb, H, 1, False, 0, d, Kp=1).view(4 * H)
             grads[f"{prefix}bias_ih_l{l}{suf}"] = gbd
             grads[f"{prefix}bias_hh_l{l}{suf}"] = gbd
-            hT = _lib.transpose_shift_f16(lay["h16"], d * Hp, Hp, shift=B if d == 0 else -B)
+            # dW_hh pairs dG_t with h_{t-1} (forward) / h_{t+1} (reverse): a shift of B rows, zero outside the sequence
             dWhh_p = torch.empty(4 * Hp, Hp, device=dev, dtype=torch.float32)
-            _lib.gemm_f16_ex(dgT[d * 4 * Hp:(d + 1) * 4 * Hp], hT, None, dWhh_p, 4 * Hp, Hp, Mp, Hp, out_scale=inv)
+            _lib.gemm_f16_rows(dg16[:, d * 4 * Hp:(d + 1) * 4 * Hp], lay["h16"][:, d * Hp:(d + 1) * Hp], dWhh_p,
+                               4 * Hp, Hp, M, y_row_shift=-B if d == 0 else B, out_scale=inv)
             grads[f"{prefix}weight_hh_l{l}{suf}"] = _lib.unpack_lstm_grad(dWhh_p, H, H, False, 0, 0)
         if l > 0 or want_dx0:
             wihT = _lib.transpose_shift_f16(wih_p, 0, kp_in)

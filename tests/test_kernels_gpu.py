@@ -40,6 +40,30 @@ def test_gemm_plain_epilogues(lib, M, N, K, epi):
     np.testing.assert_allclose(got, ref, atol=2e-5 * max(1.0, np.abs(ref).max()))
 
 
+@pytest.mark.parametrize("M,N,Kc,shift,col0", [(4864, 1216, 1300, 0, 0), (2432, 608, 777, -32, 608), (2432, 608, 640, 32, 0),
+                                               (520, 192, 130, 0, 64), (128, 64, 64, -3, 0), (304, 96, 1000, 5, 8)])
+def test_gemm_rows_mode_vs_fp64(lib, M, N, Kc, shift, col0):
+    """weight-gradient form: out = scale * X^T Y with the contraction over the ROWS of two row-major fp16 buffers read in
+    place (MN-major UMMA operands), Y shifted by whole rows (zero outside) and taken as a column slice of a wider buffer"""
+    rng = np.random.RandomState(M + N + Kc)
+    X = rng.standard_normal((Kc, M)).astype(np.float16)
+    Yw = rng.standard_normal((Kc, col0 + N + 8)).astype(np.float16)
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(Yw).cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    scale = torch.tensor([0.25], device="cuda")
+    lib.gemm_f16_rows(Xd, Yd[:, col0:col0 + N], out, M, N, Kc, y_row_shift=shift, out_scale=scale)
+    Y = Yw[:, col0:col0 + N].astype(np.float64)
+    Ys = np.zeros_like(Y)
+    if shift >= 0:
+        Ys[:Kc - shift] = Y[shift:]
+    else:
+        Ys[-shift:] = Y[:Kc + shift]
+    ref = 0.25 * X.astype(np.float64).T @ Ys
+    got = out.cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 2e-5 * np.sqrt(Kc) * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("B,T,F,D,K", [(3, 50, 129, 40, 1216), (2, 70, 33, 20, 128), (5, 26, 9, 8, 64)])
 def test_gemm_l2norm_remap_epilogue(lib, B, T, F, D, K):
     rng = np.random.RandomState(B * T)
