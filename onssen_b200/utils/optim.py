@@ -49,6 +49,17 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
 
+    def __getstate__(self):
+        # the device pointer tables are a cache keyed on live tensors: never pickled (checkpoints pickle the optimizer)
+        st = super().__getstate__() if hasattr(super(), "__getstate__") else dict(self.__dict__)
+        st = dict(st)
+        st.pop("_tables", None)
+        return st
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
