@@ -3,9 +3,6 @@
 // A (activations) and W (weights) are fp16, K-major, fed by TMA (128B swizzle) into a 4-stage
 // shared-memory ring; tcgen05.mma (kind::f16, M=128, N<=256, K=16) accumulates fp32 in TMEM with two
 // accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1. Persistent: one CTA / SM.
-// CTAs run as CLUSTERS OF TWO on vertically adjacent tiles (m_blk = 2*pair + rank, same n_blk): each CTA loads half of
-// the shared W tile and TMA-multicasts it to both, so a k-block costs 32 KB of L2 reads per SM instead of 48 -- at
-// 128x256 tiles the kernel was L2-bandwidth-bound (85 flop per L2 byte x ~10.8 TB/s = ~0.92 PFLOP/s, measured 0.96).
 //
 // Used for (reference call sites it replaces):
 //   * LSTM input projections W_ih x_t + b_ih + b_hh for all t at once   (torch nn.LSTM inside
@@ -92,6 +89,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int BN = p.block_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -101,7 +99,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full_bar[i], 1);
-        mbar_init(&empty_bar[i], 2);   // released by BOTH CTAs of the cluster (the W half-tiles are multicast)
+        mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
@@ -116,11 +114,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t crank = cluster_ctarank();
-  const int mpairs = (p.num_m_blocks + 1) / 2;
-  const int num_pairs = mpairs * p.num_n_blocks;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to it
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -128,29 +121,26 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = A_STAGE_BYTES + (uint32_t)BN * BK * 2;
-      for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
-        const int m_blk = 2 * (pt % mpairs) + (int)crank;   // may be one past the end (odd count): zero-filled rows
-        const int n_blk = pt / mpairs;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks;
+        const int n_blk = tile / p.num_m_blocks;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);           // both CTAs have consumed this stage
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.mn_major) {
             const int nbox_b = (BN + 63) / 64;
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 + nbox_b) * 8192u);
             for (int j = 0; j < 2; ++j)
               tma_load_2d(smem_a + stage * A_STAGE_BYTES + j * 8192, &tmap_a, &full_bar[stage], m_blk * BM + 64 * j,
                           kb * BK);
-            // rows outside [0, K) (time shift) and columns >= N are zero-filled; boxes alternate between the two CTAs
-            for (int j = (int)crank; j < nbox_b; j += 2)
-              tma_load_2d_mc(smem_b + stage * B_STAGE_BYTES + j * 8192, &tmap_w, &full_bar[stage], n_blk * BN + 64 * j,
-                             kb * BK + p.b_row_shift, 3);
+            for (int j = 0; j < nbox_b; ++j)   // rows outside [0, K) (time shift) and columns >= N are zero-filled
+              tma_load_2d(smem_b + stage * B_STAGE_BYTES + j * 8192, &tmap_w, &full_bar[stage], n_blk * BN + 64 * j,
+                          kb * BK + p.b_row_shift);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-          // this CTA's half of the W tile (BN/2 rows x 128 B), delivered to both CTAs
-          tma_load_2d_mc(smem_b + stage * B_STAGE_BYTES + crank * (uint32_t)(BN / 2) * 128u, &tmap_w, &full_bar[stage],
-                         kb * BK, n_blk * BN + (int)crank * (BN / 2), 3);
+          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &full_bar[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -163,7 +153,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -191,7 +181,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
             }
           }
-          umma_commit_mc(&empty_bar[stage], 3);   // releases the stage in both CTAs
+          umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);
@@ -205,11 +195,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.N & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int it = 0;
-    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m_blk = 2 * (pt % mpairs) + (int)crank;
-      const int n_blk = pt / mpairs;
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
       const int m0 = m_blk * BM + q * 32;
       const int n0 = n_blk * BN;
       // this tile's bias slice -> warp-private smem (overlaps the wait for the accumulator)
@@ -329,7 +319,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before_sync();
   __syncthreads();
-  cluster_sync_all();   // the peer may still multicast into this CTA's stages / arrive on its barriers
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -400,18 +389,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cu
       return ONSSEN_ERR_CUDA;
     attr_set = true;
   }
-  const int pairs = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
-  const int max_clusters = onssen::num_sms() / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters));
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc05_kernel<D>, ta, tw, p) == cudaSuccess ? ONSSEN_OK : ONSSEN_ERR_CUDA;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < onssen::num_sms() ? tiles : onssen::num_sms();
+  gemm_tc05_kernel<D><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tw, p);
+  return cudaGetLastError() == cudaSuccess ? ONSSEN_OK : ONSSEN_ERR_CUDA;
 }
 
 }  // namespace
@@ -439,7 +420,7 @@ int gemm_f16(const void* A, const void* W, const float* bias, float* out, int M,
   CUtensorMap ta, tw;
   int rc = make_tmap_f16(&ta, A, M, K, lda, BM);
   if (rc != ONSSEN_OK) return rc;
-  rc = make_tmap_f16(&tw, W, N, K, ldw, bn / 2);   // each CTA of a pair loads (and multicasts) half of the W tile
+  rc = make_tmap_f16(&tw, W, N, K, ldw, bn);
   if (rc != ONSSEN_OK) return rc;
   if (epi == 3) {
     switch (group) {

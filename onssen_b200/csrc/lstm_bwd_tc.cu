@@ -39,10 +39,18 @@ constexpr size_t BT_MIN_SMEM = 120 * 1024;          // > half of an SM's shared 
 long long* g_tc_trace = nullptr;
 int g_tc_sm_reserve = 0;   // SMs left free for concurrent kernels (NCCL all-reduce of the layer above), see bwd_tc_set_sm_reserve
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // 16 bytes into another CTA's shared memory; the receiver's mbarrier counts the bytes when they have landed
 __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, float a, float b, float c, float d, uint32_t bar_cluster) {
