@@ -57,10 +57,10 @@ class trainer:
     def _resume(self, checkpoint_path):
         saved = torch.load(os.path.join(checkpoint_path, "final.mdl"), weights_only=False)
         self.model.load_state_dict(saved["model"])
-        # Adam moments and step count continue where they stopped (the reference pickles the optimizer object, :120, and
-        # never reads it back; here the state_dict saved next to it is restored)
-        if saved.get("optimizer_state") is not None:
-            self.optimizer.load_state_dict(saved["optimizer_state"])
+        # Adam moments and step count continue where they stopped: the reference pickles the optimizer object (:120) and
+        # never reads it back; the checkpoint keeps exactly its keys, the state is taken from that object
+        if saved.get("optimizer") is not None and hasattr(saved["optimizer"], "state_dict"):
+            self.optimizer.load_state_dict(saved["optimizer"].state_dict())
         self.epoch = saved["epoch"] + 1
         self.min_loss = saved["cv_loss"]
         self.early_stop_count = saved["early_stop_count"]
@@ -141,7 +141,6 @@ class trainer:
             self.min_loss = cv_loss
             if self.rank == 0:
                 torch.save({'model': self.model.state_dict(), 'epoch': epoch, 'optimizer': self.optimizer,
-                            'optimizer_state': self.optimizer.state_dict(),
                             'cv_loss': self.min_loss, 'early_stop_count': self.early_stop_count},
                            os.path.join(self.checkpoint_path, "final.mdl"))
             if self.verbose:

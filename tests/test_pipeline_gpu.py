@@ -81,6 +81,14 @@ def test_trainer_validate_and_tester_eval(cuda_device, tmp_path):
     rec = t.masked_istft(lab[0], lab[1], ones, lab[2].shape[2])
     mix = lab[2][0].sum(0)
     assert (rec[0, 0] - mix).abs().max().item() < 2e-4 * mix.abs().max().item() + 1e-4   # s1+s2 == mix up to int16 rounding
+    # resume: model, epoch AND the Adam state continue (taken from the optimizer object the reference's checkpoint pickles)
+    args2 = A(dict(args))
+    args2["resume_from_checkpoint"] = "True"
+    args2["optimizer"] = ob.utils.build_optimizer(args.model.parameters(), args.optimizer_options)
+    tr2 = ob.utils.trainer(args2)
+    p0 = next(iter(args.model.parameters()))
+    assert tr2.epoch == 1 and int(tr2.optimizer.state[p0]["step"]) == int(args.optimizer.state[p0]["step"]) > 0
+    assert torch.equal(tr2.optimizer.state[p0]["exp_avg"], args.optimizer.state[p0]["exp_avg"])
 
 
 def test_loader_decodes_and_resamples_on_the_device(cuda_device, tmp_path):
