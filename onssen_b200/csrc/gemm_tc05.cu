@@ -21,13 +21,23 @@ using namespace tc05;
 
 constexpr int BM = 128;
 constexpr int BK = 64;        // fp16 elements = 128 B = one swizzle row
-constexpr int STAGES = 4;
 constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;   // 32 KB
 constexpr int EPI_PITCH_MAX = 44;                // floats per staged row (D<=40 + 4 pad, or 32+4)
 constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH_MAX;
-constexpr int NUM_THREADS = 192;                 // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+// Two shapes of the same kernel, chosen by the host from K:
+//   EW = 4 epilogue warps, 4 stages of 48 KB: long-K products (weight gradients, dgrad) whose tile time is MMA / L2 time;
+//   EW = 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks / D-groups), 3 stages: K <= 2048
+//          (forward projections, heads).  With one epilogue warp per scheduler every dependent instruction waited out
+//          its full latency (ncu: 17 % of the issue slots used, stall reason 'wait') and a 128x256 tile took ~19 k
+//          cycles to drain -- longer than its MMAs at K = 1216.
+__host__ __device__ constexpr int gemm_stages(int ew) { return ew == 8 ? 3 : 4; }
+__host__ __device__ constexpr int gemm_threads(int ew) { return (2 + ew) * 32; }   // warp0 TMA, warp1 MMA+TMEM, epilogue
+__host__ __device__ constexpr size_t gemm_smem_bytes(int ew) {
+  return 1024 /*align slack*/ + (size_t)gemm_stages(ew) * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)ew * EPI_WARP_FLOATS * 4 +
+         (size_t)ew * MAX_BN * 4 /*per-warp bias tile*/ + 256;
+}
 constexpr int TMEM_COLS = 512;
 
 struct GemmParams {
@@ -49,9 +59,6 @@ struct GemmParams {
   int b_row_shift;         // rows mode: B row k + b_row_shift pairs with A row k (time shift of the W_hh gradient)
 };
 
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
-                              4 * EPI_WARP_FLOATS * 4 + 4 * MAX_BN * 4 /*per-warp bias tile*/ + 256;
-
 __device__ __forceinline__ float act_apply(float x, int epi) {
   if (epi == 1) return 1.0f / (1.0f + __expf(-x));
   if (epi == 2) return fmaxf(x, 0.0f);
@@ -68,17 +75,18 @@ __device__ __forceinline__ void tmem_ld_group(uint32_t taddr, uint32_t* v) {
   if constexpr ((D % 8) >= 4) { tmem_ld4(taddr + o, v + o); o += 4; }
 }
 
-template <int D>  // D = 0: no l2norm path compiled in
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int D, int EPI_WARPS>  // D = 0: no l2norm path compiled in
+__global__ void __launch_bounds__(gemm_threads(EPI_WARPS), 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const GemmParams p) {
+  constexpr int STAGES = gemm_stages(EPI_WARPS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  float* bias_stage = epi_stage + 4 * EPI_WARP_FLOATS;   // [4 warps][MAX_BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_stage + 4 * MAX_BN);
+  float* bias_stage = epi_stage + EPI_WARPS * EPI_WARP_FLOATS;   // [warp][MAX_BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_stage + EPI_WARPS * MAX_BN);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -103,7 +111,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 4);
+        mbar_init(&tempty_bar[i], EPI_WARPS);
       }
       fence_mbar_init();
     }
@@ -188,8 +196,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (4 warps) =====================
+    // ===================== epilogue (EPI_WARPS warps) =====================
+    constexpr int NSEL = EPI_WARPS / 4;           // warps per TMEM lane quarter
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;             // which of the NSEL warps of that quarter: chunks hsel, hsel+NSEL, ..
     float* stg = epi_stage + (warp - 2) * EPI_WARP_FLOATS;
     float* bias_s = bias_stage + (warp - 2) * MAX_BN;
     const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.N & 3) == 0) &&
@@ -226,7 +236,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (D > 0) {
           constexpr int PITCH = D + 4;
           const int ngroups = BN / D;
-          for (int g = 0; g < ngroups; ++g) {
+          for (int g = hsel; g < ngroups; g += NSEL) {
             const int nb = n0 + g * D;
             if (nb >= p.N) break;   // warp-uniform
             uint32_t v[D];
@@ -263,7 +273,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       } else {
         constexpr int PITCH = 36;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        // this lane writes column group c4 = lane & 7 of rows 4*i + lane/8: output row offsets once per tile
+        long long roff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + 4 * i + (lane >> 3);
+          roff[i] = m < p.M ? out_row_off(m) : -1;
+        }
+        for (int c0 = 32 * hsel; c0 < BN; c0 += 32 * NSEL) {
           const int nb = n0 + c0;
           if (nb >= p.N) break;   // warp-uniform
           uint32_t v[32];
@@ -293,13 +310,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           const int ncols = min(32, min(BN - c0, p.N - nb));
           if (vec_ok) {
-            for (int idx = lane; idx < 32 * 8; idx += 32) {
-              const int r = idx >> 3;
-              const int c4 = idx & 7;
-              const int m = m0 + r;
-              if (m < p.M && c4 * 4 < ncols) {
-                const float4 o4 = *reinterpret_cast<const float4*>(stg + r * PITCH + c4 * 4);
-                *reinterpret_cast<float4*>(p.out + out_row_off(m) + nb + c4 * 4) = o4;
+            const int c4 = lane & 7;
+            if (c4 * 4 < ncols) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (roff[i] >= 0) {
+                  const float4 o4 = *reinterpret_cast<const float4*>(stg + (4 * i + (lane >> 3)) * PITCH + c4 * 4);
+                  *reinterpret_cast<float4*>(p.out + roff[i] + nb + c4 * 4) = o4;
+                }
               }
             }
           } else {
@@ -380,19 +398,25 @@ int pick_block_n(int N, int epi, int group) {
   return ((N + 15) / 16) * 16;
 }
 
-template <int D>
-int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t stream) {
+template <int D, int EW>
+int launch_ew(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc05_kernel<D, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gemm_smem_bytes(EW)) != cudaSuccess)
       return ONSSEN_ERR_CUDA;
     attr_set = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < onssen::num_sms() ? tiles : onssen::num_sms();
-  gemm_tc05_kernel<D><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tw, p);
+  gemm_tc05_kernel<D, EW><<<grid, gemm_threads(EW), gemm_smem_bytes(EW), stream>>>(ta, tw, p);
   return cudaGetLastError() == cudaSuccess ? ONSSEN_OK : ONSSEN_ERR_CUDA;
+}
+
+template <int D>
+int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t stream) {
+  // short K: the tile drains slower than it is computed -> 8 epilogue warps; long K: 4 stages of operands matter more
+  return p.K <= 2048 ? launch_ew<D, 8>(ta, tw, p, stream) : launch_ew<D, 4>(ta, tw, p, stream);
 }
 
 }  // namespace
