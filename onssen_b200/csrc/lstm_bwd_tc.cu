@@ -29,8 +29,11 @@ namespace {
 
 using namespace tc05;
 
-constexpr int BT_WORKERS = 8;
-constexpr int BT_THREADS = (BT_WORKERS + 1) * 32;   // 8 worker warps + 1 MMA warp
+#ifndef BT_WORKERS_N
+#define BT_WORKERS_N 8    // worker warps.  16 (one column per finalising thread) helped the forward kernel but not this
+#endif                    // one: 2.93 -> 3.05 us/step at cfg2 (the gather's last warp arrives later, 96 registers spill)
+constexpr int BT_WORKERS = BT_WORKERS_N;
+constexpr int BT_THREADS = (BT_WORKERS + 1) * 32;   // + 1 MMA warp
 constexpr int BT_A_COL = 128;                       // first TMEM column of the resident slab
 constexpr int BT_NACC = 2;                          // independent accumulators (see lstm_rec.cu)
 constexpr int BT_TRACE_S0 = 100;
@@ -99,6 +102,7 @@ __device__ __forceinline__ __half to_half_flag_range(float x) {   // clamp to th
 }
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  if constexpr (N == 4) tmem_ld4(taddr, v);
   if constexpr (N == 8) tmem_ld8(taddr, v);
   if constexpr (N == 16) tmem_ld16(taddr, v);
 }
@@ -111,8 +115,8 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
 
 template <int NBP>
 __global__ void __launch_bounds__(BT_THREADS, 1) lstm_bwd_tc_kernel(const BwdParams p, const int S, const int Bs) {
-  constexpr int ITEMS = NBP / 8;     // batch columns per finalising thread
-  constexpr int NBH = NBP / 2;       // accumulator columns per worker warp
+  constexpr int ITEMS = NBP / BT_WORKERS;          // batch columns per finalising thread (1, 2 or 4)
+  constexpr int NBH = NBP / (BT_WORKERS / 4);      // accumulator columns per worker warp (4 warps cover the 128 lanes)
   constexpr int PITCH = NBP + 4;     // floats per (source CTA, unit) row of the receive tile (16-byte rows, few bank conflicts)
   constexpr int GT = BT_WORKERS * 32;
   constexpr int RX_PAR = 4 * 32 * PITCH;
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) lstm_bwd_tc_kernel(const BwdPar
     // ===================== worker warps =====================
     const float inv_scale = p.scale2[1], scale = p.scale2[0];
     const float keep_scale = p.dropout_p > 0.f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
-    // TMEM role: lane quarter q (= destination CTA of the reduce-scatter), column half
+    // TMEM role: lane quarter q (= destination CTA of the reduce-scatter), column group `half` of NBH columns
     const int q = warp & 3, half = warp >> 2;
     const bool dst_has = ub * 128 + 32 * q < Hp;
     // finalise role: unit ul of this CTA's 32, columns cg*ITEMS .. +ITEMS
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) lstm_bwd_tc_kernel(const BwdPar
     }
     // gather bookkeeping: 16-byte chunk c = kc*NBP + n of the K quarter, thread handles c = tid + GT*i
     const int nchunks = Hp * NBP / 8;
-    constexpr int MAXCH = NBP == 16 ? 6 : 12;
+    constexpr int MAXCH = (768 * NBP / 8 + GT - 1) / GT;   // Hp <= 768
     const int my_chunks = (nchunks - tid + GT - 1) / GT;
     unsigned int want_mask = 0;
     for (int i = 0; i < my_chunks; ++i)
@@ -364,7 +368,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) lstm_bwd_tc_kernel(const BwdPar
           const float* rp = rx_read + par * RX_PAR;
 #pragma unroll
           for (int src_cta = 0; src_cta < 4; ++src_cta) {
-            if constexpr (ITEMS == 2) {
+            if constexpr (ITEMS == 1) {
+              rsum[0] += rp[src_cta * 32 * PITCH];
+            } else if constexpr (ITEMS == 2) {
               const float2 w2 = *reinterpret_cast<const float2*>(rp + src_cta * 32 * PITCH);
               rsum[0] += w2.x; rsum[1] += w2.y;
             } else {
@@ -399,19 +405,29 @@ __global__ void __launch_bounds__(BT_THREADS, 1) lstm_bwd_tc_kernel(const BwdPar
       }
       // rows 4u..4u+3 of column n are half of the 16-byte chunk (kc = u/2, n): lanes (ul, ul^1) swap one column
       // each so that every lane issues ONE 16-byte store per column pair
-#pragma unroll
-      for (int i = 0; i < ITEMS; i += 2) {
-        const uint2 mine_keep = (lane & 1) ? ov[i + 1] : ov[i];
-        const uint2 mine_send = (lane & 1) ? ov[i] : ov[i + 1];
+      if constexpr (ITEMS == 1) {
+        // one column per thread: the even lane of a unit pair stores the pair's chunk
         uint2 got;
-        got.x = __shfl_xor_sync(0xffffffffu, mine_send.x, 1);
-        got.y = __shfl_xor_sync(0xffffffffu, mine_send.y, 1);
-        const int ii = i + (lane & 1);
-        if (s + 1 < T && (valid_items & (1u << ii))) {
-          const int col = cg * ITEMS + ii;
-          const uint4 chunk = (lane & 1) ? make_uint4(got.x | fww, got.y | fww, mine_keep.x | fww, mine_keep.y | fww)
-                                         : make_uint4(mine_keep.x | fww, mine_keep.y | fww, got.x | fww, got.y | fww);
-          st_relaxed_v4(xt_w + ((size_t)(u >> 1) * NBP + col) * 16, chunk);
+        got.x = __shfl_xor_sync(0xffffffffu, ov[0].x, 1);
+        got.y = __shfl_xor_sync(0xffffffffu, ov[0].y, 1);
+        if (s + 1 < T && (valid_items & 1u) && !(lane & 1))
+          st_relaxed_v4(xt_w + ((size_t)(u >> 1) * NBP + cg) * 16,
+                        make_uint4(ov[0].x | fww, ov[0].y | fww, got.x | fww, got.y | fww));
+      } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i += 2) {
+          const uint2 mine_keep = (lane & 1) ? ov[i + 1] : ov[i];
+          const uint2 mine_send = (lane & 1) ? ov[i] : ov[i + 1];
+          uint2 got;
+          got.x = __shfl_xor_sync(0xffffffffu, mine_send.x, 1);
+          got.y = __shfl_xor_sync(0xffffffffu, mine_send.y, 1);
+          const int ii = i + (lane & 1);
+          if (s + 1 < T && (valid_items & (1u << ii))) {
+            const int col = cg * ITEMS + ii;
+            const uint4 chunk = (lane & 1) ? make_uint4(got.x | fww, got.y | fww, mine_keep.x | fww, mine_keep.y | fww)
+                                           : make_uint4(mine_keep.x | fww, mine_keep.y | fww, got.x | fww, got.y | fww);
+            st_relaxed_v4(xt_w + ((size_t)(u >> 1) * NBP + col) * 16, chunk);
+          }
         }
       }
       if (tid == 0) BT_TRACE(8);
