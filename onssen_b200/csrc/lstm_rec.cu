@@ -34,6 +34,9 @@ using namespace tc05;
 // takes 8 / 12 / 16 warps (4 warps cover the 128 TMEM lanes).  (Round 1 ran 32-column slices on 8 warps, 16 columns per
 // thread: 43 KB of SASS, more than the 32 KB instruction cache the step body streams through once per step.)
 // The SIMT validation path keeps 8 warps.
+#ifndef ONSSEN_REC_PREFETCH_AFTER
+#define ONSSEN_REC_PREFETCH_AFTER 0   // A/B knob: issue the step-(s+2) gate prefetch after the gather instead of before it
+#endif
 #ifndef ONSSEN_REC_GW16
 #define ONSSEN_REC_GW16 16    // gate warps of the 16-column instantiation: 16 = 4 columns per thread (measured at cfg2:
 #endif                        // 8 warps 2.37 us/step, 16 warps 2.27 -- four warps per scheduler hide the dependent-issue
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const
           if (p.h_raw) p.h_raw[o] = __float2half_rn(hval[ci]);
         }
       }
-      {
+      auto prefetch_gates = [&]() {
         // rotate the prefetch registers and issue the loads for step s+2
         const int tn = (s + 2 < T) ? (dir ? t - 2 : t + 2) : t;   // clamped: the last two loads are unused
 #pragma unroll
@@ -438,7 +441,8 @@ __global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const
           gpre[j] = gnext[j];
           gnext[j] = __ldcs(gcol + ((long long)tn * (CHUNK ? p.Bp : p.B) + jcl[j]) * ldg);
         }
-      }
+      };
+      if (!ONSSEN_REC_PREFETCH_AFTER) prefetch_gates();
       if (s + 1 < T) {
         // gather h_t of the whole group (all nrb producers) into the smem operand tile: spin on the flag bits
         uint4 v[MAXCH];
@@ -475,6 +479,7 @@ __global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const
         }
         if (tid == 0) REC_TRACE(13);
       }
+      if (ONSSEN_REC_PREFETCH_AFTER) prefetch_gates();
     }
   }
 
