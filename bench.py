@@ -354,7 +354,7 @@ def time_gpu_reference(torch, dev, ob, dev_batches, K, W):
 
 def time_disk_training(torch, ob, dev, model, opt, K):
     """Training steps fed FROM DISK through the data plugin: a temporary wsj0-2mix-layout corpus of
-    synthetic 16-bit wavs (128 utterances x {mix,s1,s2}, each read 5x per epoch = 20 steps), `wsj0_2mix_dataloader` (thread-pool PCM staging two
+    synthetic 16-bit wavs (128 utterances x {mix,s1,s2}, each read 25x per epoch = 100 steps), `wsj0_2mix_dataloader` (thread-pool PCM staging two
     batches ahead, decode + featurizer on the device), forward + loss + backward + clip + Adam; WALL CLOCK per step
     over whole epochs, first epoch untimed."""
     import shutil
@@ -373,8 +373,8 @@ def time_disk_training(torch, ob, dev, model, opt, K):
         fo = dict(data_path=root, batch_size=B, frame_length=T_FRAMES, sampling_rate=8000, window_size=CFG["n_fft"],
                   hop_size=CFG["hop"], db_threshold=DB)
         loader = ob.data.wsj0_2mix_dataloader("dc", fo, "tr", dev)
-        loader.file_list = loader.file_list * 5          # 20 steps per epoch (a real epoch has hundreds): the start-up
-                                                         # of the staging thread is paid once per epoch, as in training
+        loader.file_list = loader.file_list * 25         # 100 steps per epoch (wsj0-2mix tr has 625 at this batch size):
+                                                         # the start-up of the staging thread is paid once per epoch
 
         def epoch():
             n = 0

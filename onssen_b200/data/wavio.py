@@ -144,13 +144,17 @@ class PcmStager:
         pitch = int(lengths.max())
         item = dict(rate=rate, channels=ch, names=names, lengths=torch.from_numpy(lengths))
         if all(d[2] == "i2" for d in dec) and self.transform is None:
-            buf = _pinned(torch.zeros(nsig, B, pitch * ch, dtype=torch.int16))
+            # page-locked block straight from torch's caching host allocator (no pageable copy, no full memset: only
+            # the tail behind each utterance is zeroed)
+            buf = (torch.empty(nsig, B, pitch * ch, dtype=torch.int16, pin_memory=True) if torch.cuda.is_available()
+                   else torch.empty(nsig, B, pitch * ch, dtype=torch.int16))
             view = buf.numpy()
 
             def put(i):
                 b, k = divmod(i, nsig)
                 n = lengths[b]
                 view[k, b, :n * ch] = dec[i][3][:n].reshape(-1)
+                view[k, b, n * ch:] = 0
 
             list(pool.map(put, range(len(dec))))
             item["pcm"] = buf
@@ -169,6 +173,11 @@ class PcmStager:
     def __iter__(self):
         q = queue.Queue(maxsize=max(1, self.depth))
         stop = threading.Event()
+        # The decode threads run Python between their file reads; with the default 5 ms GIL switch interval one of them
+        # can hold the interpreter for milliseconds while the stepping thread waits to enqueue its next kernels.
+        import sys
+        old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(old_interval, 2e-4))
 
         def produce():
             try:
@@ -192,6 +201,7 @@ class PcmStager:
                     raise item
                 yield item
         finally:
+            sys.setswitchinterval(old_interval)
             stop.set()
             while t.is_alive():               # unblock a producer waiting on a full queue
                 try:
