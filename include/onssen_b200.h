@@ -136,6 +136,12 @@ size_t onssen_blstm_rec_workspace_bytes(int B, int H);
 int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
                          float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
                          size_t workspace_bytes, int use_tensor_cores, void* stream);
+/* Inference on a zero-padded batch of utterances with different lengths (the evaluation loop of
+ * egs/wsj0-2mix/.../evaluate.py runs batch 1; this runs B at once): frames_per_utt [B] int32 on the device. State and output
+ * of column b are held at zero for t >= frames_per_utt[b], so every utterance gets exactly its batch-1 result (the
+ * reverse direction starts at its own last frame). No dropout, tensor-core path. */
+int onssen_blstm_rec_fwd_var(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
+                             const int32_t* frames_per_utt, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Debug/profiling hook: when set to a device buffer of 64 int64, the next recurrent launches record clock64
  * stamps of CTA 0 for steps 100..103 (16 slots per step; see REC_TRACE in csrc/lstm_rec.cu). NULL disables. */

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "onssen_resample_poly": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp]),
     "onssen_blstm_rec_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_f, c_ull, c_ull, c_vp, c_sz,
                                      c_int, c_vp]),
+    "onssen_blstm_rec_fwd_var": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "onssen_bn_num_chunks": (c_int, [c_int]),
     "onssen_bn_scratch_bytes": (c_sz, [c_int, c_int]),
     "onssen_bn_forward_f16": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_int, c_vp, c_vp, c_vp,
@@ -292,10 +293,19 @@ def blstm_rec_workspace(B, H, device):
 
 
 def blstm_rec_fwd(gates, whh_p, B, T, H, y_h=None, y_f=None, dropout_p=0.0, seed=0, offset=0, workspace=None,
-                  use_tensor_cores=True):
+                  use_tensor_cores=True, col_len=None):
+    """col_len: optional int32 CUDA tensor [B], frames per utterance of a zero-padded batch (inference only)."""
     lib = load()
     if workspace is None:
         workspace = blstm_rec_workspace(B, H, gates.device)
+    if col_len is not None:
+        if dropout_p != 0.0 or not use_tensor_cores:
+            raise OnssenB200Error("per-utterance lengths are an inference feature of the tensor-core path (no dropout)")
+        rc = lib.onssen_blstm_rec_fwd_var(_p(_req(gates, torch.float32, "gates")), _p(whh_p), B, T, H, _p(y_h), _p(y_f),
+                                          _p(_req(col_len, torch.int32, "col_len")), _p(workspace), workspace.numel(),
+                                          _stream())
+        _check(rc, "onssen_blstm_rec_fwd")
+        return
     ev = None
     if REC_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

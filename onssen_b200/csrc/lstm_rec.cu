@@ -69,6 +69,8 @@ struct RecParams {
   float* act_out;    // == gates: activated i,f,g,o written in place over the consumed pre-activations
   float* c_out;      // [T*B][2*Hp] cell state
   __half* h_raw;     // [T*B][2*Hp] h before dropout (operand of the W_hh weight gradient)
+  const int* col_len; // optional (inference on padded batches): frames of every utterance; state and output of column b are
+                      // held at zero for t >= col_len[b], so the reverse direction starts at the utterance's own last frame
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -294,8 +296,12 @@ __global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const
       if (((tid + GT * i) % NBP) < nb_valid) want_mask |= 1u << i;
 
     float c_state[NBH / 4];
+    int len_ci[NBH / 4];          // frames of the utterance each of this lane's (unit, column) items belongs to
 #pragma unroll
-    for (int i = 0; i < NBH / 4; ++i) c_state[i] = 0.f;
+    for (int i = 0; i < NBH / 4; ++i) {
+      c_state[i] = 0.f;
+      len_ci[i] = p.col_len != nullptr ? p.col_len[b0 + min(jbase + 4 * i + gate, nb_valid - 1)] : T;
+    }
     // input pre-activations are prefetched TWO steps ahead (HBM latency under load exceeds the MMA phase)
     // All prefetch loads are UNCONDITIONAL (a `cond ? load : 0` select would make the warp wait for the load
     // at the select): pad columns / out-of-range steps read a valid neighbouring address and the value is
@@ -395,9 +401,10 @@ __global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const
         const float gf = xr[XP];
         const float gg = xr[2 * XP];
         const float go = xr[3 * XP];
-        const float c = fmaf(gf, c_state[ci], gi * gg);
+        const bool live = t < len_ci[ci];            // padded frames of a shorter utterance: zero state, zero output
+        const float c = live ? fmaf(gf, c_state[ci], gi * gg) : 0.f;
         c_state[ci] = c;
-        const float h = go * (FAST ? tanh_fast(c) : fmaf(2.0f, sigmoid_f(2.0f * c), -1.0f));
+        const float h = live ? go * (FAST ? tanh_fast(c) : fmaf(2.0f, sigmoid_f(2.0f * c), -1.0f)) : 0.f;
         hval[ci] = h;
         // publish: the 8 units of this warp (one k-chunk) x column j form one 16-byte chunk of the operand
         // tile; they sit in the 8 lanes that share this gate index.  Assemble the chunk with a 3-level
@@ -580,7 +587,7 @@ extern "C" size_t onssen_blstm_rec_workspace_bytes(int B, int H) {
 static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
                         float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
                         size_t workspace_bytes, int use_tensor_cores, void* stream, float* act_out, float* c_out,
-                        void* h_raw);
+                        void* h_raw, const int* col_len = nullptr);
 
 extern "C" int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B, int T, int H, void* y_h,
                                     float* y_f, float dropout_p, unsigned long long seed,
@@ -588,6 +595,14 @@ extern "C" int onssen_blstm_rec_fwd(const float* gates, const void* whh_p, int B
                                     int use_tensor_cores, void* stream) {
   return rec_fwd_impl(gates, whh_p, B, T, H, y_h, y_f, dropout_p, seed, offset, workspace, workspace_bytes,
                       use_tensor_cores, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int onssen_blstm_rec_fwd_var(const float* gates, const void* whh_p, int B, int T, int H, void* y_h,
+                                        float* y_f, const int32_t* frames_per_utt, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (!frames_per_utt) return ONSSEN_ERR_ARG;
+  return rec_fwd_impl(gates, whh_p, B, T, H, y_h, y_f, 0.f, 0, 0, workspace, workspace_bytes, 1, stream, nullptr, nullptr,
+                      nullptr, frames_per_utt);
 }
 
 extern "C" int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p, int B, int T, int H, void* y_h,
@@ -602,7 +617,7 @@ extern "C" int onssen_blstm_rec_fwd_train(float* gates_inout, const void* whh_p,
 static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int H, void* y_h, float* y_f,
                         float dropout_p, unsigned long long seed, unsigned long long offset, void* workspace,
                         size_t workspace_bytes, int use_tensor_cores, void* stream, float* act_out, float* c_out,
-                        void* h_raw) {
+                        void* h_raw, const int* col_len) {
   if (!gates || !whh_p || !workspace || B <= 0 || T <= 0 || H <= 0) return ONSSEN_ERR_ARG;
   if (!y_h && !y_f) return ONSSEN_ERR_ARG;
   if (dropout_p < 0.f || dropout_p >= 1.f) return ONSSEN_ERR_ARG;
@@ -638,6 +653,7 @@ static int rec_fwd_impl(const float* gates, const void* whh_p, int B, int T, int
     p.act_out = act_out ? act_out + og : nullptr;
     p.c_out = c_out ? c_out + oy : nullptr;
     p.h_raw = h_raw ? (__half*)h_raw + oy : nullptr;
+    p.col_len = col_len ? col_len + c0 : nullptr;
     p.hash_off = (unsigned int)oy;
     p.B = bc; p.S = sp.S; p.Bs = sp.Bs;
     const size_t hbuf_bytes = (size_t)2 * 2 * sp.S * p.Hp * sp.NBP * 2;

@@ -126,19 +126,26 @@ class _WavBatchLoader:
 
 
 class _EvalLoader(_WavBatchLoader):
-    """batch 1, full-length features + mixture STFT + reference signals (:170-254, repaired)."""
+    """full-length features + mixture STFT + reference signals (:170-254, repaired).  Batch 1 like the reference by
+    default; `feature_options.eval_batch_size` > 1 (an extra key) zero-pads B utterances of different lengths into one
+    batch and appends their sample counts as a 4th label element -- `utils.tester` then runs the model once per batch
+    with per-utterance lengths in the recurrence and post-processes every utterance at its own length."""
 
     def _featurize(self, mix, s1, s2, lengths):
         from .. import _lib
         fo = self.fo
         n_fft, hop = _opt(fo, "window_size"), _opt(fo, "hop_size")
-        ns = int(lengths[0])
+        B = mix.shape[0]
+        ns = int(lengths.max())
         frames = 1 + ns // hop
-        o = _lib.stft_features(mix, None, None, n_fft, hop, torch.zeros(1, dtype=torch.int32), frames,
+        o = _lib.stft_features(mix, None, None, n_fft, hop, torch.zeros(B, dtype=torch.int32), frames,
                                ["feature", "ph_mix"], lengths=lengths)
         ph = o["ph_mix"]
-        sig_ref = torch.stack([s1[0, :ns], s2[0, :ns]], 0).unsqueeze(0)          # (1, 2, nsample)
-        return [o["feature"]], [ph[..., 0].contiguous(), ph[..., 1].contiguous(), sig_ref]
+        sig_ref = torch.stack([s1[:, :ns], s2[:, :ns]], 1)                       # (B, 2, nsample of the longest)
+        label = [ph[..., 0].contiguous(), ph[..., 1].contiguous(), sig_ref]
+        if B > 1:
+            label.append(lengths.to(torch.int32))                                 # host tensor: samples per utterance
+        return [o["feature"]], label
 
 
 def wsj0_2mix_dataloader(model_name, feature_options, partition, device=None, rank=0, world_size=1):
@@ -146,5 +153,7 @@ def wsj0_2mix_dataloader(model_name, feature_options, partition, device=None, ra
         return _WavBatchLoader(model_name, feature_options, partition, device, _opt(feature_options, "batch_size"), True,
                                rank, world_size)
     if partition == "tt":
-        return _EvalLoader(model_name, feature_options, partition, device, 1, False, rank, world_size)
+        eb = (feature_options.get("eval_batch_size", 1) if isinstance(feature_options, dict)
+              else getattr(feature_options, "eval_batch_size", 1))
+        return _EvalLoader(model_name, feature_options, partition, device, int(eb), False, rank, world_size)
     raise ValueError(partition)

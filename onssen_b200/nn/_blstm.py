@@ -76,14 +76,27 @@ def require_no_grad(module_name, *tensors):
             "(there is deliberately no autograd/PyTorch fallback)")
 
 
-def blstm_forward(rnn, cache, x, training, want_f32, want_f16, use_tensor_cores=True):
-    """x (B,T,I) fp32 CUDA. Returns (y_h fp16 [T*B][2Hp] or None, y_f fp32 [T*B][2Hp] or None)."""
+def blstm_forward(rnn, cache, x, training, want_f32, want_f16, use_tensor_cores=True, lengths=None):
+    """x (B,T,I) fp32 CUDA. Returns (y_h fp16 [T*B][2Hp] or None, y_f fp32 [T*B][2Hp] or None).
+    lengths: optional int32 CUDA tensor (B,) of frames per utterance (zero-padded inference batch)."""
     B, T, _ = x.shape
     return blstm_forward_packed(rnn, cache, _lib.pack_input_f16(x.contiguous()), B, T, training, want_f32,
-                                want_f16, use_tensor_cores)
+                                want_f16, use_tensor_cores, lengths)
 
 
-def blstm_forward_packed(rnn, cache, a, B, T, training, want_f32, want_f16, use_tensor_cores=True):
+def eval_lengths(model, B, device):
+    """frames per utterance set by the batched evaluation loop (`model.frame_lengths`, utils/test.py), or None"""
+    lens = getattr(model, "frame_lengths", None)
+    if lens is None:
+        return None
+    if model.training:
+        raise _lib.OnssenB200Error("frame_lengths (padded batches) are supported in eval() mode only")
+    lens = torch.as_tensor(lens, dtype=torch.int32, device=device)
+    assert lens.numel() == B, "frame_lengths must have one entry per utterance"
+    return lens
+
+
+def blstm_forward_packed(rnn, cache, a, B, T, training, want_f32, want_f16, use_tensor_cores=True, lengths=None):
     """Same, from an already packed time-major fp16 input a [T*B][Kp]."""
     assert rnn.bidirectional and rnn.batch_first and rnn.proj_size == 0
     H, L = rnn.hidden_size, rnn.num_layers
@@ -103,6 +116,6 @@ def blstm_forward_packed(rnn, cache, a, B, T, training, want_f32, want_f16, use_
         y_f = torch.empty(M, 2 * Hp, device=x.device, dtype=torch.float32) if (last and want_f32) else None
         p = float(rnn.dropout) if (training and not last) else 0.0
         seed = _next_seed() if p > 0 else 0
-        _lib.blstm_rec_fwd(gates, whh_p, B, T, H, y_h, y_f, p, seed, l, ws, use_tensor_cores)
+        _lib.blstm_rec_fwd(gates, whh_p, B, T, H, y_h, y_f, p, seed, l, ws, use_tensor_cores, col_len=lengths)
         a = y_h
     return y_h, y_f

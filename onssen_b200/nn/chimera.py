@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward
+from ._blstm import eval_lengths, PackCache, blstm_forward
 
 
 class chimera(nn.Module):
@@ -32,7 +32,7 @@ class chimera(nn.Module):
         H, D, S = self.hidden_dim, self.embedding_dim, self.num_speaker
         M = T * B
         y_h, _ = blstm_forward(self.rnn, self._rnn_cache, x, self.training, want_f32=False, want_f16=True,
-                               use_tensor_cores=self.use_tensor_cores)
+                               use_tensor_cores=self.use_tensor_cores, lengths=eval_lengths(self, x.shape[0], x.device))
         wdc = self._dc_cache.get([self.fc_dc.weight], lambda: _lib.pack_linear_f16(self.fc_dc.weight, True, H))
         wmi = self._mi_cache.get([self.fc_mi.weight], lambda: _lib.pack_linear_f16(self.fc_mi.weight, True, H))
         emb = torch.empty(B, T, F, D, device=x.device, dtype=torch.float32)

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ._blstm import PackCache, blstm_forward, bn_sync
+from ._blstm import PackCache, blstm_forward, bn_sync, eval_lengths
 
 
 class deep_clustering(nn.Module):
@@ -35,7 +35,7 @@ class deep_clustering(nn.Module):
         H, D = self.hidden_dim, self.embedding_dim
         M = T * B
         _, y_f = blstm_forward(self.rnn, self._rnn_cache, x, self.training, want_f32=True, want_f16=False,
-                               use_tensor_cores=self.use_tensor_cores)
+                               use_tensor_cores=self.use_tensor_cores, lengths=eval_lengths(self, B, x.device))
         bn = self.bn
         a_h, _, _ = _lib.bn_forward_f16(y_f, M, H, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
                                         bn.running_var, bn.eps, bn.momentum, self.training, sync=bn_sync(self))

@@ -61,10 +61,29 @@ class tester:
         self.model = self.model.eval()
         with torch.no_grad():
             for input, label in self.test_loader:
-                output = self.model(input)
-                sig_est, sig_ref = self.get_est_sig(input, label, output)
-                sdr = batch_si_sdr(sig_est, sig_ref)                          # (B,) like batch_SDR_torch
-                sdrs.update(float(sdr.mean().item()), sdr.numel())
+                B = input[0].shape[0]
+                if B == 1:                                                    # the reference's loop (batch 1)
+                    output = self.model(input)
+                    sig_est, sig_ref = self.get_est_sig(input, label, output)
+                    sdr = batch_si_sdr(sig_est, sig_ref)                      # (B,) like batch_SDR_torch
+                    sdrs.update(float(sdr.mean().item()), sdr.numel())
+                    continue
+                # zero-padded batch of utterances of different lengths (eval_batch_size > 1): one model call with the
+                # per-utterance frame counts in the recurrence, then every utterance at its own length
+                ns = label[3]
+                frames = 1 + ns.to(torch.int64) // self.hop_size
+                self.model.frame_lengths = frames.to(torch.int32)
+                try:
+                    output = self.model(input)
+                finally:
+                    self.model.frame_lengths = None
+                for b in range(B):
+                    fb, nb = int(frames[b]), int(ns[b])
+                    inp_b = [x[b:b + 1, :fb] for x in input]
+                    lab_b = [label[0][b:b + 1, :fb], label[1][b:b + 1, :fb], label[2][b:b + 1, :, :nb]]
+                    out_b = [o[b:b + 1, :fb] for o in output]
+                    sig_est, sig_ref = self.get_est_sig(inp_b, lab_b, out_b)
+                    sdrs.update(float(batch_si_sdr(sig_est, sig_ref).mean().item()), 1)
         return sdrs.avg
 
 

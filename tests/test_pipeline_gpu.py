@@ -91,6 +91,46 @@ def test_trainer_validate_and_tester_eval(cuda_device, tmp_path):
     assert torch.equal(tr2.optimizer.state[p0]["exp_avg"], args.optimizer.state[p0]["exp_avg"])
 
 
+@pytest.mark.parametrize("model_name", ["dc", "chimera"])
+def test_batched_evaluation_equals_batch_one(cuda_device, tmp_path, model_name):
+    """`eval_batch_size` > 1: utterances of different lengths zero-padded into one batch, per-utterance frame counts in
+    the recurrence (state held at zero beyond an utterance's end, so the reverse direction starts at its own last
+    frame).  Every utterance must get the outputs -- and the SI-SDR -- of the reference's batch-1 loop
+    (egs/wsj0-2mix/*/evaluate.py)."""
+    import onssen_b200 as ob
+    _make_corpus(tmp_path, n_utt=3)                      # 9000, 9640, 10280 samples: 141 / 151 / 161 frames
+    torch.manual_seed(3)
+    fo = dict(data_path=str(tmp_path), batch_size=2, frame_length=100, sampling_rate=8000, window_size=256, hop_size=64,
+              db_threshold=40)
+    model = (ob.nn.deep_clustering(129, 64, 2, 20) if model_name == "dc" else ob.nn.chimera(129, 64, 2, 20))
+    model = model.to(cuda_device).eval()
+    one = ob.data.wsj0_2mix_dataloader(model_name, fo, "tt", cuda_device)
+    many = ob.data.wsj0_2mix_dataloader(model_name, dict(fo, eval_batch_size=3), "tt", cuda_device)
+    singles = list(one)
+    (inp, lab), = list(many)
+    assert inp[0].shape[0] == 3 and len(lab) == 4 and lab[3].tolist() == [9000, 9640, 10280]
+    frames = (1 + lab[3].to(torch.int64) // 64).tolist()
+    with torch.no_grad():
+        model.frame_lengths = torch.tensor(frames, dtype=torch.int32)
+        out = model(inp)
+        model.frame_lengths = None
+        for b, (inp1, lab1) in enumerate(singles):
+            out1 = model(inp1)
+            fb = frames[b]
+            assert inp1[0].shape[1] == fb
+            assert torch.equal(inp[0][b, :fb], inp1[0][0])                       # same features as the batch-1 loader
+            for o, o1 in zip(out, out1):
+                assert (o[b, :fb] - o1[0]).abs().max().item() < 2e-6             # same arithmetic per utterance
+    ckpt = tmp_path / "ckpt"
+    os.makedirs(ckpt, exist_ok=True)
+    torch.save({"model": model.state_dict()}, ckpt / "final.mdl")
+    T = ob.utils.tester_dc if model_name == "dc" else ob.utils.tester_chimera
+    args = dict(model_name=model_name, device=str(cuda_device), model=model, checkpoint_path=str(ckpt), feature_options=fo)
+    sdr1 = T(dict(args, test_loader=one)).eval()
+    sdr3 = T(dict(args, test_loader=many)).eval()
+    assert np.isfinite(sdr1) and abs(sdr1 - sdr3) < 1e-3, (sdr1, sdr3)
+
+
 def test_loader_decodes_and_resamples_on_the_device(cuda_device, tmp_path):
     """16 kHz stereo int16 files with feature_options.sampling_rate = 8000: raw PCM staged by the thread pool, int16 ->
     float mono and the polyphase resampling on the device; waveforms must equal scipy.signal.resample_poly of the host
