@@ -14,6 +14,7 @@
 #include "tc05.cuh"
 #include "common.cuh"
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace {
 
@@ -398,6 +399,25 @@ int pick_block_n(int N, int epi, int group) {
   return ((N + 15) / 16) * 16;
 }
 
+// Tile width for a problem of m_blocks x N: 256 columns unless that leaves SMs idle in the last (or only) wave -- the
+// W_hh weight gradients (2432 x 608 outputs, K = 12800) are 57 tiles of 128x256 on 148 SMs.  Cost model: waves x (BN + 64)
+// (the 128-row A tile is loaded per k-block whatever BN is).
+int pick_block_n_fill(int m_blocks, int N) {
+  const int sms = onssen::num_sms();
+  const int widest = pick_block_n(N, 0, 0);
+  static const bool enabled = []() { const char* e = getenv("ONSSEN_GEMM_FILL"); return !(e && e[0] == '0'); }();
+  if (!enabled) return widest;      // ONSSEN_GEMM_FILL=0: always the widest tile (A/B switch)
+  int best = widest;
+  long long best_cost = -1;
+  for (int bn : {widest, 192, 128, 96, 64}) {
+    if (bn > widest) continue;
+    const long long tiles = (long long)m_blocks * ((N + bn - 1) / bn);
+    const long long cost = ((tiles + sms - 1) / sms) * (bn + 64);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 template <int D, int EW>
 int launch_ew(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
@@ -472,7 +492,7 @@ int gemm_f16_rows(const void* X, const void* Y, float* out, int M, int N, int Kc
     return ONSSEN_ERR_ARG;
   GemmParams p;
   p.M = M; p.N = N; p.K = Kc; p.bias = nullptr; p.out = out; p.ld_out = ld_out; p.epi = 0; p.group = 0;
-  p.remap_inner = 0; p.remap_outer = 0; p.block_n = pick_block_n(N, 0, 0);
+  p.remap_inner = 0; p.remap_outer = 0; p.block_n = pick_block_n_fill((M + BM - 1) / BM, N);
   p.out_scale = out_scale; p.inv_norm = nullptr;
   p.mn_major = 1; p.b_row_shift = y_row_shift;
   p.num_m_blocks = (M + BM - 1) / BM;

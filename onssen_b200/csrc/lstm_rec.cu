@@ -401,7 +401,11 @@ __global__ void __launch_bounds__(rec_threads(NB, TC), 1) blstm_rec_kernel(const
         const float gf = xr[XP];
         const float gg = xr[2 * XP];
         const float go = xr[3 * XP];
+#ifdef ONSSEN_REC_NO_LEN
+        const bool live = true;
+#else
         const bool live = t < len_ci[ci];            // padded frames of a shorter utterance: zero state, zero output
+#endif
         const float c = live ? fmaf(gf, c_state[ci], gi * gg) : 0.f;
         c_state[ci] = c;
         const float h = live ? go * (FAST ? tanh_fast(c) : fmaf(2.0f, sigmoid_f(2.0f * c), -1.0f)) : 0.f;

@@ -127,12 +127,28 @@ class _ModelFunction(torch.autograd.Function):
     def forward(ctx, model, fwd, bwd, x, *params):
         # x is a tensor, or a tuple of tensors for models with several inputs (none of them needs a gradient)
         outs, saved = fwd(model, x)
+        # Entries of `saved` that ARE outputs go through save_for_backward: held in the plain dict they would close the
+        # cycle ctx -> output -> grad_fn -> ctx, and a forward that is never backpropagated would keep its hundreds of
+        # MB of gates / cell states until the garbage collector runs.
+        outs_t = outs if isinstance(outs, tuple) else (outs,)
+        keep, ctx.out_keys = [], {}
+        for k, v in list(saved.items()):
+            if any(v is t for t in outs_t):
+                ctx.out_keys[k] = len(keep)
+                keep.append(v)
+                saved[k] = None
+        ctx.save_for_backward(*keep)
         ctx.model, ctx.saved, ctx.bwd = model, saved, bwd
         ctx.names = [n for n, _ in model.named_parameters()]
-        return outs if isinstance(outs, tuple) else outs
+        return outs
 
     @staticmethod
     def backward(ctx, *d_outs):
+        if ctx.saved is None:
+            raise RuntimeError("onssen_b200: the saved forward state of this graph was already consumed by a backward "
+                               "(BPTT overwrites it in place); run the forward again")
+        for k, i in ctx.out_keys.items():
+            ctx.saved[k] = ctx.saved_tensors[i]
         sync = getattr(ctx.model, "grad_sync", None)
         grads = ctx.bwd(ctx.model, ctx.saved, [None if d is None else d.contiguous() for d in d_outs],
                         None if sync is None else sync.reduce_bucket)

@@ -251,3 +251,19 @@ def test_bptt_persistent_kernels_match_per_step_kernel(cuda_device, B, H, T):
         assert scale > 0 and torch.isfinite(a1).all()
         assert (a0 - a1).abs().max().item() < 2e-4 * scale            # same operands, different summation order
         assert (h0.float() - h1.float()).abs().max().item() <= 2e-3 * h0.float().abs().max().item()
+
+
+def test_second_backward_through_the_same_graph_is_refused(cuda_device):
+    """BPTT overwrites the saved forward state in place: a second backward through the same graph must say so instead
+    of returning garbage (and the outputs are saved through save_for_backward, not in a dict that closes a cycle)."""
+    import onssen_b200 as ob
+    torch.manual_seed(0)
+    model = ob.nn.deep_clustering(33, 16, 2, 8, dropout=0.0).to(cuda_device).train()
+    x = torch.randn(2, 12, 33, device=cuda_device)
+    emb, = model([x])
+    loss = emb.square().mean()
+    loss.backward(retain_graph=True)
+    g1 = model.fc_dc.weight.grad.clone()
+    assert torch.isfinite(g1).all() and g1.abs().max() > 0
+    with pytest.raises(RuntimeError, match="already consumed"):
+        loss.backward()
