@@ -239,15 +239,21 @@ def _scalar(x):
 
 
 def event_ms(torch, fn, n, barrier):
+    """-> (total ms of n calls by CUDA events, last result, median ms of the individual calls).  The total is what the
+    figures are computed from; the median exposes a run in which one call stalled on the host (a collector pass of the
+    interpreter, an allocator growth) -- the garbage of the previous workload is collected before the clock starts."""
+    import gc
+    gc.collect()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
     out = None
     for i in range(n):
         out = fn(i)
-    e1.record()
+        ev[i + 1].record()
     barrier()
-    return e0.elapsed_time(e1), out
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+    return ev[0].elapsed_time(ev[n]), out, per[n // 2]
 
 
 def time_workload(torch, ob, wl, dev, rank, world, barrier, K, W, grad_sync=None):
@@ -278,10 +284,10 @@ def time_workload(torch, ob, wl, dev, rank, world, barrier, K, W, grad_sync=None
     with torch.no_grad():
         for i in range(W):
             fwd(i)
-        ms_f, lf = event_ms(torch, fwd, K, barrier)
+        ms_f, lf, med_f = event_ms(torch, fwd, K, barrier)
     for i in range(min(W, 3)):
         train(i)
-    ms_t, lt = event_ms(torch, train, K, barrier)
+    ms_t, lt, med_t = event_ms(torch, train, K, barrier)
     t = torch.tensor([ms_f, ms_t], device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -289,6 +295,7 @@ def time_workload(torch, ob, wl, dev, rank, world, barrier, K, W, grad_sync=None
     out = {"workload": wl["desc"], "batch_per_gpu": B, "steps": K,
            "fwd_loss_ms": t[0].item() / K, "fwd_loss_utt_s": world * B * K / (t[0].item() / 1e3),
            "train_ms": t[1].item() / K, "train_utt_s": world * B * K / (t[1].item() / 1e3),
+           "fwd_loss_ms_median_step": med_f, "train_ms_median_step": med_t,
            "loss_fwd": _scalar(lf), "loss_train": _scalar(lt)}
     del model, opt, batches
     torch.cuda.empty_cache()
@@ -335,10 +342,10 @@ def time_gpu_reference(torch, dev, ob, dev_batches, K, W):
     with torch.no_grad():
         for i in range(W):
             fwd(i)
-        ms_f, lf = event_ms(torch, fwd, K, sync)
+        ms_f, lf, _ = event_ms(torch, fwd, K, sync)
     for i in range(min(W, 3)):
         train(i)
-    ms_t, lt = event_ms(torch, train, K, sync)
+    ms_t, lt, _ = event_ms(torch, train, K, sync)
     B = CFG["B"]
     out = {"what": "reference onssen.nn.deep_clustering + onssen.loss.loss_dc (oracle/_ref, unmodified) .to('cuda'): "
                    "cuDNN LSTM / cuBLAS / ATen, fp32, train-mode BN, dropout 0.3; model + loss only (no featurizer)",
