@@ -1,7 +1,11 @@
 // BPTT for one BLSTM layer (autograd of torch.nn.LSTM as used at onssen/nn/deep_clustering.py:34-35; the
 // reference gets it from cuDNN through loss.backward(), onssen/utils/train.py:82).
 //
-// One launch per time step (both directions), no inter-CTA synchronisation inside a launch: CTA (unit block,
+// This file: the mma.sync kernels -- the per-step kernel (validation partner of the differential tests) and the
+// persistent kernel of round 1 (fallback for shapes the tcgen05 cluster kernel of lstm_bwd_tc.cu does not take) -- the
+// W_hh^T packing for both implementations, and the C entry point that dispatches between the three.
+//
+// Per-step kernel: one launch per time step (both directions), no inter-CTA synchronisation inside a launch: CTA (unit block,
 // dir, batch block) owns 32 hidden units.  It first forms dh_rec[u][b] = sum_r W_hh[r][u] * dG_{prev}[r][b]
 // over ALL 4H gate rows of the previously processed step (mma.sync m16n8k16, fp16 operands, W_hh^T slice and
 // dG read from L2, K split over the 8 warps), then does the gate math for ITS units at this step and writes

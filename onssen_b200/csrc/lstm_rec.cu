@@ -12,16 +12,20 @@
 // row, two fp16 per 32-bit column: 304 of the 512 TMEM columns at H=600) and stays there for the whole
 // sequence as the A operand of tcgen05.mma (TS form): recurrent weights cross HBM once per layer and are
 // never re-streamed through shared memory.  Per step:
-//   control thread : relaxed-poll the group's arrival counter (all nrb CTAs published h_{t-1}), one acquire
-//                    fence -> cp.async.bulk h_{t-1} [NBP x Hp fp16, pre-laid-out as UMMA B operand] into
-//                    smem -> Hp/16 x tcgen05.mma (A: TMEM, B: smem, D: TMEM; M=128, N=NBP, K=16) -> commit
-//   8 gate warps   : tcgen05.ld their TMEM lanes (thread = one gate row, NB/2 batch columns), add the
-//                    prefetched input pre-activation, sigmoid/tanh (tanh(x) = 2*sigmoid(2x)-1 so all gates
-//                    share code), exchange activated gates through a warp-private smem tile (the 4 gates of a
-//                    unit are 4 adjacent lanes), update c (registers) and h, store h_t (fp16) into the group's
-//                    exchange buffer, bar.sync, ONE release-increment of the counter, and only then write the
-//                    layer output (off the critical path).
-// Latency-bound by the per-step serial chain (publish -> poll -> bulk copy -> MMA -> gate math), not by bytes.
+//   MMA warp       : (converged, elected lane issues) waits on a named barrier until the gate warps have written the
+//                    h_{t-1} tile [NBP x Hp fp16, UMMA B-operand layout] to smem -> Hp/16 x tcgen05.mma (A: TMEM,
+//                    B: smem, D: 2 TMEM accumulators; M=128, N=NBP, K=16) -> tcgen05.commit to an mbarrier
+//   gate warps     : (16 / 12 / 16 warps for 16 / 24 / 32-column slices) tcgen05.ld their TMEM lanes (thread = one gate
+//                    row x 4 or 8 batch columns), add the input pre-activation prefetched two steps ahead, activate
+//                    (inference: one tanh.approx per value; training forward: ex2 + rcp), exchange activated gates
+//                    through a warp-private smem tile (the 4 gates of a unit are 4 adjacent lanes), update c
+//                    (registers) and h, PUBLISH h_t: 16-byte relaxed stores into the group's L2-resident exchange
+//                    tile with bit 14 of every fp16 (always 0 for |h| <= 1) carrying the step parity -- the data
+//                    validate themselves, no counter, no fence; write the layer output and issue the prefetch;
+//                    GATHER: spin on 16-byte relaxed loads of all nrb producers' chunks until their flag bits are
+//                    this step's, strip the flag, write the next step's operand tile, fence.proxy.async, bar.arrive.
+// Latency-bound by the per-step serial chain (MMA issue -> TMEM load + gate math -> publish -> gather), not by bytes;
+// DESIGN.md section 4.1 and profiles/r02_exchange_experiments.md hold the measured anatomy and the rejected variants.
 #include "tc05.cuh"
 #include "common.cuh"
 

@@ -3,8 +3,9 @@
 
 Replaces what `loss_avg.backward()` (/root/reference/onssen/utils/train.py:82) gets from cuDNN/cuBLAS autograd
 for deep_clustering.py:34-42 and chimera.py:35-45: F.normalize / sigmoid backward -> head dgrad/wgrad (tcgen05
-GEMMs on scaled fp16 copies) -> BatchNorm backward -> per layer BPTT (one launch per step) + W_ih / W_hh / bias
-gradients (tcgen05 GEMMs contracting over all (t,b)) + dgrad to the layer below."""
+GEMMs on scaled fp16 copies) -> BatchNorm backward -> per layer BPTT (ONE persistent tcgen05 launch per layer, both
+directions, all T steps: csrc/lstm_bwd_tc.cu) + W_ih / W_hh / bias gradients (rows-mode tcgen05 GEMMs contracting over
+all (t,b), operands read in place) + dgrad to the layer below."""
 import torch
 
 from .. import _lib
