@@ -35,39 +35,42 @@ class GradSync:
             from .. import _lib
             _lib.load().onssen_blstm_rec_bwd_set_sm_reserve(int(os.environ.get("ONSSEN_DDP_SM_RESERVE", "48")))
 
-    def _launch_nccl(self, tensors):
-        # ONE grouped launch of in-place AVG all-reduces (ncclGroupStart/End through torch's coalescing manager): no
-        # flatten copy, no copy-back, no divide pass
-        with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
-            for t in tensors:
-                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
-        return cm
+    def _launch(self, names, grads):
+        """one collective over a bucket -> an entry of self.pending"""
+        tensors = [grads[n] for n in names]
+        if self.nccl:
+            # ONE grouped launch of in-place AVG all-reduces (ncclGroupStart/End through torch's coalescing manager): no
+            # flatten copy, no copy-back, no divide pass
+            with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+            return (cm, None, names, grads)
+        # other backends (gloo in the CPU tests): flatten, SUM, and write the average back in wait()
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return (work, flat, names, grads)
 
     def reduce_bucket(self, grads):
-        """grads: dict name -> tensor (final).  NCCL: grouped in-place AVG all-reduces, launched now (overlap) or all
-        together in wait().  Other backends (gloo in the CPU tests): flatten, SUM, and write the average back in
-        wait()."""
+        """grads: dict name -> tensor (final).  Launched now (overlap) or held back until flush() / wait()."""
         if self.world == 1 or not grads:
             return
         names = sorted(grads)
-        tensors = [grads[n] for n in names]
-        self.bytes_reduced += sum(t.numel() * t.element_size() for t in tensors)
-        if self.nccl:
-            if self.overlap:
-                self.pending.append((self._launch_nccl(tensors), None, names, grads))
-            else:
-                self.deferred.extend(tensors)
-            return
-        flat = torch.cat([t.reshape(-1) for t in tensors])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.pending.append((work, flat, names, grads))
+        self.bytes_reduced += sum(grads[n].numel() * grads[n].element_size() for n in names)
+        if self.overlap:
+            self.pending.append(self._launch(names, grads))
+        else:
+            self.deferred.append((names, grads))
 
     def flush(self):
-        """Launch the all-reduce of the buckets held back so far (called by the backward once its last cooperative
-        kernel is enqueued: the collective then runs beside the remaining weight-gradient GEMMs)."""
+        """Launch the all-reduce of the buckets held back so far as ONE collective (called by the backward once its
+        last cooperative kernel is enqueued: the collective then runs beside the remaining weight-gradient GEMMs)."""
         if self.deferred:
-            self.pending.append((self._launch_nccl(self.deferred), None, None, None))
+            merged = {}
+            for names, grads in self.deferred:
+                for n in names:
+                    merged[n] = grads[n]
             self.deferred = []
+            self.pending.append(self._launch(sorted(merged), merged))
 
     def wait(self):
         """Blocks (the stream, for NCCL) until every bucket is reduced; afterwards the tensors hold the rank average."""

@@ -54,6 +54,24 @@ def _worker(rank, world, port, ret):
     assert torch.allclose(g1["fc.weight"], torch.full((3, 4), avg)) and torch.allclose(g1["fc.bias"], torch.arange(4.0) * avg)
     assert torch.allclose(g2["rnn.weight_ih_l0"], torch.ones(6, 2) * 10 * avg) and torch.allclose(gb, torch.full((5,), avg))
     assert sync.bytes_reduced == (12 + 4 + 12 + 5) * 4
+    # deferred mode (the NCCL default): buckets are held back, flush() launches ONE collective over all of them (the
+    # backward calls it once its last cooperative kernel is enqueued), wait() finishes it
+    held = GradSync(overlap=False)
+    h1 = {"fc.weight": torch.full((3, 4), float(rank + 1))}
+    h2 = {"rnn.weight_hh_l0": torch.full((2, 2), 3.0 * (rank + 1)), "rnn.bias_ih_l0": torch.arange(3.0) * (rank + 1)}
+    held.reduce_bucket(h1)
+    held.reduce_bucket(h2)
+    assert not held.pending and len(held.deferred) == 2
+    assert float(h1["fc.weight"][0, 0]) == float(rank + 1)            # nothing reduced yet
+    held.flush()
+    assert len(held.pending) == 1 and not held.deferred
+    held.flush()                                                      # idempotent
+    assert len(held.pending) == 1
+    held.wait()
+    assert torch.allclose(h1["fc.weight"], torch.full((3, 4), avg))
+    assert torch.allclose(h2["rnn.weight_hh_l0"], torch.full((2, 2), 3.0 * avg))
+    assert torch.allclose(h2["rnn.bias_ih_l0"], torch.arange(3.0) * avg)
+    assert held.bytes_reduced == (12 + 4 + 3) * 4 and not held.pending
     lin = torch.nn.Linear(3, 2)
     with torch.no_grad():
         lin.weight.fill_(float(rank))
