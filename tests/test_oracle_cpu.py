@@ -71,6 +71,27 @@ def test_oracle_stft_matches_torch(n_fft, hop, ns):
     assert np.abs(y - yt).max() <= 1e-5 * np.abs(mix).max() + 1e-7
 
 
+@pytest.mark.parametrize("n_fft,hop,ns", [(256, 64, 8000), (512, 128, 9000), (1024, 256, 20000)])
+def test_oracle_stft_matches_scipy(n_fft, hop, ns):
+    """second, independent restatement of the librosa boundary (rows a1 / a19 are unpinned: librosa is not installable):
+    scipy.signal.stft with the periodic Hann window, 'even' (= reflect) boundary extension and its 1/sum(window) scaling
+    undone must give the oracle's spectrum; scipy.signal.istft the oracle's waveform."""
+    from scipy import signal
+    x = O.synth_utterance(3, ns)[0]
+    spec = O.stft(x, n_fft, hop)
+    win = signal.get_window("hann", n_fft, fftbins=True)
+    _, _, z = signal.stft(x.astype(np.float64), window=win, nperseg=n_fft, noverlap=n_fft - hop, boundary="even",
+                          padded=False, return_onesided=True)
+    z = z.T * win.sum()
+    assert z.shape[0] >= spec.shape[0]
+    assert np.abs(spec - z[:spec.shape[0]]).max() <= 2e-6 * np.abs(z).max()
+    y = O.istft(spec, hop, ns)
+    _, y2 = signal.istft((spec / win.sum()).T, window=win, nperseg=n_fft, noverlap=n_fft - hop, boundary=True,
+                         input_onesided=True)
+    n = min(len(y), len(y2)) - n_fft                     # scipy stops at the last whole hop: compare the common part
+    assert n > 0 and np.abs(y[:n] - y2[:n]).max() <= 1e-6 * np.abs(x).max() + 1e-7
+
+
 def test_oracle_frame_indexing_and_labels():
     # 4 s @ 8 kHz -> 501 frames, crop start exclusive bound 101 (np.random.randint(frames - T))
     assert O.num_crop_starts(32000, 64, 400) == 101
